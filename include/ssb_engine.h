@@ -1,0 +1,75 @@
+/* ssb_engine.h — C ABI of the engine core (libssb_core.so): what both drop-in surfaces are built on, plus the
+ * batch extension the headline metric is measured on (the reference has no batched call), table
+ * dumps for parity tests, and the device-side hooks of the multi-GPU path. Plain pointers and sizes only. */
+#ifndef SSB_ENGINE_H
+#define SSB_ENGINE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ssb_index ssb_index;
+
+/* last error message of the calling thread ("" if none) */
+const char* ssb_last_error(void);
+/* number of CUDA kernels launched by the engine since process start */
+uint64_t ssb_kernel_launches(void);
+/* binds the engine to a CUDA device (default: current device). Call once per process, before any index. */
+int ssb_set_device(int device);
+
+/* ---- index build: replaces StringIndex::StringIndex (nGramSearch.hpp:120-172) ----
+ * words: size pointers to NUL-terminated strings of char (wide=0) or wchar_t/UTF-32 (wide=1), NULL allowed;
+ * weight: per word or NULL; rowBase: global index of the first row (key-range shards). NULL on failure. */
+ssb_index* ssb_index_create(const void* const* words, uint64_t size, uint16_t rowSize, const float* weight, uint16_t gSize,
+                            int wide, uint64_t rowBase);
+/* same, from a packed buffer: units (1 or 4 bytes each), offsets[size+1] in units, isNull[size] (may be NULL) */
+ssb_index* ssb_index_create_packed(const void* units, const uint64_t* offsets, const uint8_t* isNull, uint64_t size,
+                                   uint16_t rowSize, const float* weight, uint16_t gSize, int wide, uint64_t rowBase);
+void ssb_index_destroy(ssb_index* ix);
+uint64_t ssb_index_size(const ssb_index* ix);      /* getSize    (nGramSearch.hpp:488) */
+uint64_t ssb_index_lib_size(const ssb_index* ix);  /* getLibSize (nGramSearch.hpp:496) */
+void ssb_index_set_valid_char(ssb_index* ix, const char* chars, int n);   /* dllmain.cpp:142 */
+
+/* info[]: 0 K keys, 1 T terms, 2 E edges, 3 G grams, 4 P postings, 5 nShort, 6 symBits, 7 A, 8 identity, 9 uniformW,
+ * 10 gSize, 11 unit bytes, 12 indexed, 13 term units, 14 key units (incl. terminators), 15 device bytes,
+ * 16 gram windows before de-dup, 17 packed gram sort */
+void ssb_index_info(const ssb_index* ix, uint64_t info[24]);
+/* build timings in ms: 0 total, 1 host pack, 2 H2D, 3 intern, 4 edges, 5 strings+grams, 6 D2H */
+void ssb_index_build_ms(const ssb_index* ix, double ms[8]);
+/* copies a device/host table to dst (bytes must match exactly). which:
+ * 0 gramCodes u64[G]  1 gramOff u32[G+1]  2 postings u32[P]  3 termOff u32[T+1]  4 termChars units
+ * 5 termEdgeOff u32[T+1]  6 edgeKid u32[E]  7 edgeW f32[E]  8 keyOff u32[K+1]  9 keyChars units  10 keyRow u64[K]
+ * 11 symTable u32[256 | A]  12 shortTerms u32[nShort] */
+int ssb_index_copy(const ssb_index* ix, int which, void* dst, uint64_t bytes);
+
+/* ---- batched search: replaces StringIndex::_search per query (nGramSearch.hpp:350-404) ---- */
+typedef struct ssb_batch {
+	uint32_t nq;
+	uint32_t* offsets;      /* [nq+1] CSR into the arrays below */
+	uint32_t* kids;         /* rank id of the key inside the index (order: length asc, first occurrence asc) */
+	float* scores;
+	uint64_t* rows;         /* global first row of the key */
+	const void** strings;   /* NUL-terminated key strings (char or wchar_t), aliasing index storage */
+} ssb_batch;
+/* queries: nq NUL-terminated strings. limit 0 = unlimited. Returns NULL on failure. */
+ssb_batch* ssb_search_batch(ssb_index* ix, const void* const* queries, uint32_t nq, float threshold, uint32_t limit);
+/* same, from packed units + offsets[nq+1] */
+ssb_batch* ssb_search_batch_packed(ssb_index* ix, const void* units, const uint32_t* offsets, uint32_t nq, float threshold,
+                                   uint32_t limit);
+void ssb_batch_free(ssb_batch* b);
+
+/* re-runs the device part of the last uploaded batch (queries resident in HBM, results left in HBM);
+ * ms[0] = whole device part, ms[1] = k_fast_search alone (CUDA events on the engine's stream).
+ * stats[]: 0 nFast 1 nDense 2 nOverflow 3 postings touched by fast queries */
+int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uint32_t limit, float ms[2], uint64_t stats[4]);
+
+/* ---- multi-GPU (key-range shards, one process per GPU): fixed-size per-query records for an all-gather ----
+ * record = { u32 scoreBits, u32 keyLen, u64 row, u64 keyHash } (24 bytes); a query's unused slots have row = ~0.
+ * d_out / d_gathered / d_merged are DEVICE pointers: [nq][limit] per shard, shards concatenated on gather. */
+int ssb_export_records(ssb_index* ix, uint32_t nq, uint32_t limit, void* d_out);
+int ssb_merge_records(const void* d_gathered, uint32_t nShards, uint32_t nq, uint32_t limit, void* d_merged, uint32_t* d_counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,384 @@
+// engine.cu — host side of the engine core: packing of the caller's char**/wchar_t** into pinned CSR buffers,
+// index objects, result marshalling, and the extern "C" API of include/ssb_engine.h.
+// Mirrors the role of dllmain.cpp:22-151 + StringIndex::search/score/release (nGramSearch.hpp:415-483).
+#include "../../include/ssb_engine.h"
+#include "index.h"
+#include "search.h"
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <cwchar>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+using namespace ssb;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+struct EngineGlobals {
+	std::once_flag once;
+	int device = -1;
+	void init()
+	{
+		std::call_once(once, [&] {
+			if (device < 0) SSB_CUDA(cudaGetDevice(&device));
+			SSB_CUDA(cudaSetDevice(device));
+			cudaMemPool_t pool;
+			SSB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+			uint64_t keep = ~0ull;   // keep freed blocks cached in the pool: no OS round trips between batches
+			SSB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+		});
+		SSB_CUDA(cudaSetDevice(device));
+	}
+} g_engine;
+
+unsigned host_threads()
+{
+	unsigned n = std::thread::hardware_concurrency();
+	return std::max(1u, std::min(n ? n : 1u, 32u));
+}
+
+template <class F> void parallel_for(uint64_t n, F f)
+{
+	unsigned nt = (unsigned)std::min<uint64_t>(host_threads(), std::max<uint64_t>(1, n / 65536));
+	if (nt <= 1) { f(0, n); return; }
+	std::vector<std::thread> th;
+	uint64_t chunk = (n + nt - 1) / nt;
+	for (unsigned t = 0; t < nt; ++t) {
+		uint64_t b = t * chunk, e = std::min(n, b + chunk);
+		if (b >= e) break;
+		th.emplace_back([=] { f(b, e); });
+	}
+	for (auto& t : th) t.join();
+}
+
+inline size_t unit_len(const char* s) { return strlen(s); }
+inline size_t unit_len(const wchar_t* s) { return wcslen(s); }
+
+}   // namespace
+
+struct ssb_index {
+	DeviceIndex dix;
+	HostKeys hk;
+	SearchWorkspace ws;
+	BuildStats bst;
+	double msPack = 0;
+	uint8_t validLut[256];
+	cudaStream_t stream = nullptr;
+	std::mutex mu;            // one batch at a time per index (the workspace is shared)
+	PinBuf<uint8_t> pinQ;     // pinned staging of packed queries
+	PinBuf<uint32_t> pinQOff;
+	SearchStats lastStats;
+	~ssb_index()
+	{
+		if (stream) { cudaStreamSynchronize(stream); }
+		// device buffers are released by their destructors (stream-ordered); the stream itself is destroyed last
+	}
+};
+
+namespace {
+
+void default_valid(uint8_t lut[256])
+{
+	memset(lut, 0, 256);
+	// nGramSearch.h:307-313
+	for (const char* p = ".%$ @0123456789abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"; *p; ++p) lut[(unsigned char)*p] = 1;
+}
+
+template <class C>
+ssb_index* create_from_pointers(const C* const* words, uint64_t size, uint16_t rowSize, const float* weight, uint16_t gSize,
+                                uint64_t rowBase)
+{
+	g_engine.init();
+	auto ix = std::make_unique<ssb_index>();
+	default_valid(ix->validLut);
+	SSB_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+	auto t0 = std::chrono::steady_clock::now();
+	PackedWords pw;
+	PinBuf<uint64_t> off;
+	PinBuf<uint8_t> isNull;
+	PinBuf<C> chars;
+	PinBuf<float> wts;
+	if (words && size >= 2) {
+		off.reserve(size + 1);
+		isNull.reserve(size);
+		uint64_t* o = off.get();
+		uint8_t* nu = isNull.get();
+		// pass 1: lengths (parallel strlen over the caller's pointers)
+		parallel_for(size, [&](uint64_t b, uint64_t e) {
+			for (uint64_t i = b; i < e; ++i) {
+				const C* w = words[i];
+				nu[i] = w == nullptr;
+				o[i + 1] = w ? unit_len(w) : 0;
+			}
+		});
+		o[0] = 0;
+		for (uint64_t i = 0; i < size; ++i) o[i + 1] += o[i];
+		const uint64_t total = o[size];
+		chars.reserve(std::max<uint64_t>(total, 1));
+		C* c = chars.get();
+		// pass 2: gather code units into one pinned CSR buffer
+		parallel_for(size, [&](uint64_t b, uint64_t e) {
+			for (uint64_t i = b; i < e; ++i)
+				if (words[i]) memcpy(c + o[i], words[i], (o[i + 1] - o[i]) * sizeof(C));
+		});
+		if (weight) {
+			wts.reserve(size);
+			memcpy(wts.get(), weight, size * sizeof(float));
+		}
+		pw.chars = c; pw.off = o; pw.isNull = nu; pw.weight = weight ? wts.get() : nullptr; pw.n = size; pw.totalUnits = total;
+	}
+	ix->msPack = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	build_index(ix->dix, ix->hk, pw, rowSize, gSize, (int)sizeof(C), rowBase, ix->validLut, ix->stream, &ix->bst);
+	return ix.release();
+}
+
+ssb_index* create_from_packed(const void* units, const uint64_t* offsets, const uint8_t* isNull, uint64_t size, uint16_t rowSize,
+                              const float* weight, uint16_t gSize, int unitBytes, uint64_t rowBase)
+{
+	g_engine.init();
+	auto ix = std::make_unique<ssb_index>();
+	default_valid(ix->validLut);
+	SSB_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+	PackedWords pw;
+	std::vector<uint8_t> zeros;
+	if (units && offsets && size >= 2) {
+		if (!isNull) { zeros.assign(size, 0); isNull = zeros.data(); }
+		pw.chars = units; pw.off = offsets; pw.isNull = isNull; pw.weight = weight; pw.n = size; pw.totalUnits = offsets[size];
+	}
+	build_index(ix->dix, ix->hk, pw, rowSize, gSize, unitBytes, rowBase, ix->validLut, ix->stream, &ix->bst);
+	return ix.release();
+}
+
+ssb_batch* marshal(ssb_index* ix, const BatchOutput& out)
+{
+	auto* b = new ssb_batch();
+	b->nq = out.nq;
+	b->offsets = new uint32_t[out.nq + 1];
+	uint64_t total = 0;
+	for (uint32_t q = 0; q < out.nq; ++q) { b->offsets[q] = (uint32_t)total; total += out.count[q]; }
+	b->offsets[out.nq] = (uint32_t)total;
+	b->kids = new uint32_t[total ? total : 1];
+	b->scores = new float[total ? total : 1];
+	b->rows = new uint64_t[total ? total : 1];
+	b->strings = new const void*[total ? total : 1];
+	const uint8_t* chars = ix->hk.chars.data();
+	const int unit = ix->dix.unit;
+	for (uint32_t q = 0; q < out.nq; ++q) {
+		uint32_t n = out.count[q], o = b->offsets[q];
+		if (n <= out.stride) {
+			memcpy(b->kids + o, out.kid.data() + (size_t)q * out.stride, (size_t)n * 4);
+			memcpy(b->scores + o, out.score.data() + (size_t)q * out.stride, (size_t)n * 4);
+		}
+	}
+	for (auto& big : out.big) {
+		uint32_t o = b->offsets[big.first];
+		for (size_t i = 0; i < big.second.size(); ++i) { b->kids[o + i] = big.second[i].first; b->scores[o + i] = big.second[i].second; }
+	}
+	for (uint64_t i = 0; i < total; ++i) {
+		uint32_t kid = b->kids[i];
+		b->rows[i] = ix->hk.row[kid];
+		b->strings[i] = chars + (size_t)ix->hk.off[kid] * unit;
+	}
+	return b;
+}
+
+template <class F> auto guarded(F f, decltype(f()) fail) -> decltype(f())
+{
+	try {
+		g_lastError.clear();
+		return f();
+	} catch (const std::exception& e) {
+		g_lastError = e.what();
+		fprintf(stderr, "[ssb] %s\n", e.what());
+	} catch (...) {
+		g_lastError = "unknown error";
+	}
+	return fail;
+}
+
+}   // namespace
+
+extern "C" {
+
+#define SSB_API __attribute__((visibility("default")))
+
+SSB_API const char* ssb_last_error(void) { return g_lastError.c_str(); }
+SSB_API uint64_t ssb_kernel_launches(void) { return g_kernel_launches.load(); }
+SSB_API int ssb_set_device(int device)
+{
+	return guarded([&] { g_engine.device = device; g_engine.init(); return 0; }, -1);
+}
+
+SSB_API ssb_index* ssb_index_create(const void* const* words, uint64_t size, uint16_t rowSize, const float* weight, uint16_t gSize,
+                                    int wide, uint64_t rowBase)
+{
+	return guarded([&]() -> ssb_index* {
+		if (wide) return create_from_pointers<wchar_t>(reinterpret_cast<const wchar_t* const*>(words), size, rowSize, weight, gSize, rowBase);
+		return create_from_pointers<char>(reinterpret_cast<const char* const*>(words), size, rowSize, weight, gSize, rowBase);
+	}, nullptr);
+}
+SSB_API ssb_index* ssb_index_create_packed(const void* units, const uint64_t* offsets, const uint8_t* isNull, uint64_t size,
+                                           uint16_t rowSize, const float* weight, uint16_t gSize, int wide, uint64_t rowBase)
+{
+	return guarded([&]() -> ssb_index* { return create_from_packed(units, offsets, isNull, size, rowSize, weight, gSize, wide ? 4 : 1, rowBase); },
+	               nullptr);
+}
+SSB_API void ssb_index_destroy(ssb_index* ix)
+{
+	if (!ix) return;
+	guarded([&] {
+		cudaStream_t s = ix->stream;
+		delete ix;
+		if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+		return 0;
+	}, 0);
+}
+SSB_API uint64_t ssb_index_size(const ssb_index* ix) { return ix && ix->dix.indexed ? ix->dix.T : 0; }
+SSB_API uint64_t ssb_index_lib_size(const ssb_index* ix) { return ix && ix->dix.indexed ? ix->dix.G : 0; }
+SSB_API void ssb_index_set_valid_char(ssb_index* ix, const char* chars, int n)
+{
+	if (!ix) return;
+	guarded([&] {
+		std::lock_guard<std::mutex> lk(ix->mu);
+		memset(ix->validLut, 0, 256);
+		for (int i = 0; i < n; ++i) ix->validLut[(unsigned char)chars[i]] = 1;
+		if (ix->dix.validLut.get()) {
+			SSB_CUDA(cudaMemcpyAsync(ix->dix.validLut.get(), ix->validLut, 256, cudaMemcpyHostToDevice, ix->stream));
+			SSB_CUDA(cudaStreamSynchronize(ix->stream));
+		}
+		return 0;
+	}, 0);
+}
+SSB_API void ssb_index_info(const ssb_index* ix, uint64_t info[24])
+{
+	memset(info, 0, 24 * sizeof(uint64_t));
+	if (!ix) return;
+	const DeviceIndex& d = ix->dix;
+	info[0] = d.K; info[1] = d.T; info[2] = d.E; info[3] = d.G; info[4] = d.P; info[5] = d.nShort; info[6] = d.symBits; info[7] = d.A;
+	info[8] = d.identity; info[9] = d.uniformW; info[10] = d.g; info[11] = d.unit; info[12] = d.indexed;
+	info[13] = d.termUnits; info[14] = d.keyUnits;
+	info[15] = d.device_bytes(); info[16] = ix->bst.windows; info[17] = d.packed; info[18] = d.multiEdgeKeys;
+	info[19] = ix->bst.hashRetries;
+}
+SSB_API void ssb_index_build_ms(const ssb_index* ix, double ms[8])
+{
+	memset(ms, 0, 8 * sizeof(double));
+	if (!ix) return;
+	ms[0] = ix->bst.msTotal + ix->msPack; ms[1] = ix->msPack; ms[2] = ix->bst.msH2D; ms[3] = ix->bst.msIntern; ms[4] = ix->bst.msEdges;
+	ms[5] = ix->bst.msGrams; ms[6] = ix->bst.msD2H;
+}
+SSB_API int ssb_index_copy(const ssb_index* ix, int which, void* dst, uint64_t bytes)
+{
+	if (!ix) return -1;
+	return guarded([&] {
+		const DeviceIndex& d = ix->dix;
+		const void* src = nullptr;
+		uint64_t have = 0;
+		auto pick = [&](const void* p, uint64_t b) { src = p; have = b; };
+		switch (which) {
+		case 0: pick(d.gramCodes.get(), (uint64_t)d.G * 8); break;
+		case 1: pick(d.gramOff.get(), (uint64_t)(d.G + 1) * 4); break;
+		case 2: pick(d.postings.get(), (uint64_t)d.P * 4); break;
+		case 3: pick(d.termOff.get(), (uint64_t)(d.T + 1) * 4); break;
+		case 4: pick(d.termChars.get(), (uint64_t)d.termUnits * d.unit); break;
+		case 5: pick(d.termEdgeOff.get(), (uint64_t)(d.T + 1) * 4); break;
+		case 6: pick(d.edgeKid.get(), (uint64_t)d.E * 4); break;
+		case 7: pick(d.edgeW.get(), (uint64_t)d.E * 4); break;
+		case 8: pick(d.keyOff.get(), (uint64_t)(d.K + 1) * 4); break;
+		case 9: pick(d.keyChars.get(), (uint64_t)d.keyUnits * d.unit); break;
+		case 10: pick(d.keyRow.get(), (uint64_t)d.K * 8); break;
+		case 11: pick(d.symTable.get(), d.unit == 1 ? 1024 : (uint64_t)d.A * 4); break;
+		case 12: pick(d.shortTerms.get(), (uint64_t)d.nShort * 4); break;
+		default: throw std::runtime_error("ssb_index_copy: unknown table");
+		}
+		if (have != bytes) throw std::runtime_error("ssb_index_copy: size mismatch");
+		if (bytes) {
+			SSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ix->stream));
+			SSB_CUDA(cudaStreamSynchronize(ix->stream));
+		}
+		return 0;
+	}, -1);
+}
+
+SSB_API ssb_batch* ssb_search_batch_packed(ssb_index* ix, const void* units, const uint32_t* offsets, uint32_t nq, float threshold,
+                                           uint32_t limit)
+{
+	if (!ix) return nullptr;
+	return guarded([&]() -> ssb_batch* {
+		g_engine.init();
+		std::lock_guard<std::mutex> lk(ix->mu);
+		BatchOutput out;
+		search_batch(ix->dix, ix->ws, units, offsets, nq, threshold, limit, out, ix->stream, &ix->lastStats);
+		return marshal(ix, out);
+	}, nullptr);
+}
+SSB_API ssb_batch* ssb_search_batch(ssb_index* ix, const void* const* queries, uint32_t nq, float threshold, uint32_t limit)
+{
+	if (!ix) return nullptr;
+	return guarded([&]() -> ssb_batch* {
+		g_engine.init();
+		std::lock_guard<std::mutex> lk(ix->mu);
+		const int unit = ix->dix.unit;
+		ix->pinQOff.reserve(nq + 1);
+		uint32_t* off = ix->pinQOff.get();
+		uint64_t total = 0;
+		for (uint32_t q = 0; q < nq; ++q) {
+			off[q] = (uint32_t)total;
+			const void* p = queries[q];
+			total += !p ? 0 : (unit == 1 ? strlen((const char*)p) : wcslen((const wchar_t*)p));
+		}
+		off[nq] = (uint32_t)total;
+		ix->pinQ.reserve(std::max<uint64_t>(total * unit, 16));
+		for (uint32_t q = 0; q < nq; ++q)
+			if (queries[q]) memcpy(ix->pinQ.get() + (size_t)off[q] * unit, queries[q], (size_t)(off[q + 1] - off[q]) * unit);
+		BatchOutput out;
+		search_batch(ix->dix, ix->ws, ix->pinQ.get(), off, nq, threshold, limit, out, ix->stream, &ix->lastStats);
+		return marshal(ix, out);
+	}, nullptr);
+}
+SSB_API void ssb_batch_free(ssb_batch* b)
+{
+	if (!b) return;
+	delete[] b->offsets; delete[] b->kids; delete[] b->scores; delete[] b->rows; delete[] b->strings;
+	delete b;
+}
+SSB_API int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uint32_t limit, float ms[2], uint64_t stats[4])
+{
+	if (!ix) return -1;
+	return guarded([&] {
+		g_engine.init();
+		std::lock_guard<std::mutex> lk(ix->mu);
+		SearchStats st;
+		search_batch_resident(ix->dix, ix->ws, nq, threshold, limit, ix->stream, &st);
+		if (ms) { ms[0] = st.msDevice; ms[1] = st.msFastKernel; }
+		if (stats) { stats[0] = st.nFast; stats[1] = st.nDense; stats[2] = st.nOverflow; stats[3] = st.postingsTouched; }
+		return 0;
+	}, -1);
+}
+SSB_API int ssb_export_records(ssb_index* ix, uint32_t nq, uint32_t limit, void* d_out)
+{
+	if (!ix) return -1;
+	return guarded([&] {
+		g_engine.init();
+		std::lock_guard<std::mutex> lk(ix->mu);
+		export_records(ix->dix, ix->ws, nq, limit, static_cast<MergeRecord*>(d_out), ix->stream);
+		SSB_CUDA(cudaStreamSynchronize(ix->stream));
+		return 0;
+	}, -1);
+}
+SSB_API int ssb_merge_records(const void* d_gathered, uint32_t nShards, uint32_t nq, uint32_t limit, void* d_merged, uint32_t* d_counts)
+{
+	return guarded([&] {
+		g_engine.init();
+		merge_records(static_cast<const MergeRecord*>(d_gathered), nShards, nq, limit, static_cast<MergeRecord*>(d_merged), d_counts, 0);
+		SSB_CUDA(cudaStreamSynchronize(0));
+		return 0;
+	}, -1);
+}
+
+}   // extern "C"

@@ -1,0 +1,826 @@
+// search.cu — batched n-gram search on the GPU (replaces StringIndex::_search / searchLong / searchShort /
+// calcScore / partial_sort, nGramSearch.hpp:182-404).
+//
+//   k_query_prep   one warp per query: escapeBlank/trim/toUpper (hpp:372-376), gram windows -> codes (hpp:29-36),
+//                  warp match-any de-duplication with multiplicities, binary search of the sorted gram table,
+//                  integer thresholds cmin/cprom evaluated with the reference's exact float expressions.
+//   k_fast_search  persistent CTAs, one query at a time. The query's posting lists are streamed through shared
+//                  memory in term-id-aligned windows; every thread owns a term-id sub-range and does a K-way merge
+//                  of the (sorted) windows in registers, which yields (term, match count) with NO atomics and no
+//                  per-term counters. Scores use the reference's float ops ((float)c / (float)|Q|, w * s), candidates
+//                  are filtered against a running k-th best (tau) and kept in a shared-memory buffer that is reduced
+//                  with an in-CTA radix select; the final <= limit entries are bitonic-sorted. Rank key =
+//                  (score desc, kid asc) where kid already encodes (key length asc, key id asc) (nGramSearch.h:262-269).
+//   dense path     general fallback (short terms / edit-distance path hpp:182-270, wildcard hpp:356-369, long
+//                  queries, limit > FAST_KLIM, buffer overflow): per-term counters + per-key max-merge in global
+//                  memory, then a device radix sort. O(T + K) per query, exact for every input.
+#include "search.h"
+#include "primitives.cuh"
+#include "textops.cuh"
+#include <algorithm>
+#include <cmath>
+
+namespace ssb {
+
+SearchWorkspace::~SearchWorkspace()
+{
+	if (ev0) cudaEventDestroy(ev0);
+	if (ev1) cudaEventDestroy(ev1);
+	if (ev2) cudaEventDestroy(ev2);
+	if (ev3) cudaEventDestroy(ev3);
+}
+
+namespace {
+
+constexpr uint32_t INF = 0xFFFFFFFFu;
+constexpr int FS_THREADS = 256;
+constexpr int FS_WIN = 8192;                 // posting slots staged per pass
+constexpr int FS_WIN_ALLOC = FS_WIN + 64;    // + one bound/sentinel slot per list + the shared INF slot
+constexpr int FS_BUF = 4096;                 // candidate buffer entries (>= 2 * FAST_KLIM)
+constexpr int FS_FIRST_PASS = 2048;          // small first pass: establishes tau early
+
+struct IndexView {
+	int g, unit, symBits;
+	uint32_t K, T, G, A, nShort;
+	int identity, uniformW, multiEdgeKeys;
+	float wmax;
+	const uint8_t* validLut;
+	const uint32_t* symTable;
+	const uint64_t* gramCodes;
+	const uint32_t* gramOff;
+	const uint32_t* postings;
+	const uint32_t* termOff;
+	const uint8_t* termChars;
+	const uint32_t* termEdgeOff;
+	const uint32_t* edgeKid;
+	const float* edgeW;
+	const uint32_t* shortTerms;
+	const uint32_t* keyOff;
+	const uint8_t* keyChars;
+	const uint32_t* keyEdgeOff;
+	const uint32_t* keyEdgeTerm;
+	const float* keyEdgeW;
+	const float* keyWmax;
+	const uint64_t* keyRow;
+};
+
+IndexView make_view(const DeviceIndex& ix)
+{
+	IndexView v;
+	v.g = ix.g; v.unit = ix.unit; v.symBits = ix.symBits;
+	v.K = ix.K; v.T = ix.T; v.G = ix.G; v.A = ix.A; v.nShort = ix.nShort;
+	v.identity = ix.identity; v.uniformW = ix.uniformW; v.multiEdgeKeys = ix.multiEdgeKeys;
+	v.wmax = ix.wmax;
+	v.validLut = ix.validLut.get(); v.symTable = ix.symTable.get();
+	v.gramCodes = ix.gramCodes.get(); v.gramOff = ix.gramOff.get(); v.postings = ix.postings.get();
+	v.termOff = ix.termOff.get(); v.termChars = ix.termChars.get();
+	v.termEdgeOff = ix.termEdgeOff.get(); v.edgeKid = ix.edgeKid.get(); v.edgeW = ix.edgeW.get();
+	v.shortTerms = ix.shortTerms.get();
+	v.keyOff = ix.keyOff.get(); v.keyChars = ix.keyChars.get();
+	v.keyEdgeOff = ix.keyEdgeOff.get(); v.keyEdgeTerm = ix.keyEdgeTerm.get(); v.keyEdgeW = ix.keyEdgeW.get();
+	v.keyWmax = ix.keyWmax.get(); v.keyRow = ix.keyRow.get();
+	return v;
+}
+
+// the reference's score of a long-path term: (float)count / (float)grams.size()   (hpp:300)
+__device__ __forceinline__ float term_score(uint32_t c, uint32_t n) { return __fdiv_rn((float)c, (float)n); }
+// std::max(w * s, entryScore-default 0.0f) with -0.0f canonicalised (hpp:326)
+__device__ __forceinline__ float edge_value(float w, float s)
+{
+	float v = __fmul_rn(w, s);
+	return v > 0.0f ? v : 0.0f;
+}
+
+// trim(escapeBlank(key)) == query ?  The key is NOT upper-cased (hpp:330-335).
+template <class U>
+__device__ bool key_equals_query(const IndexView& ix, uint32_t kid, const U* __restrict__ q, uint32_t qlen)
+{
+	const U* key = reinterpret_cast<const U*>(ix.keyChars) + ix.keyOff[kid];
+	uint32_t b = 0, e = ix.keyOff[kid + 1] - ix.keyOff[kid] - 1;
+	while (b < e && unit_blank(key[b], ix.validLut)) ++b;
+	while (e > b && unit_blank(key[e - 1], ix.validLut)) --e;
+	if (e - b != qlen) return false;
+	for (uint32_t j = 0; j < qlen; ++j)
+		if (unit_escape(key[b + j], ix.validLut) != q[j]) return false;
+	return true;
+}
+
+// match count of the query against one long term, straight from the term's characters:
+// sum over query windows (duplicates kept) of [window gram occurs in the term]   (hpp:289-298 restated per term)
+template <class U>
+__device__ uint32_t count_for_term(const IndexView& ix, uint32_t t, const uint64_t* __restrict__ qcode, uint32_t nGrams)
+{
+	const U* tc = reinterpret_cast<const U*>(ix.termChars);
+	uint32_t b = ix.termOff[t], len = ix.termOff[t + 1] - b;
+	if (len < 2u * ix.g) return 0;
+	const uint64_t mask = (ix.g * ix.symBits >= 64) ? ~0ull : ((1ull << (ix.g * ix.symBits)) - 1);
+	uint64_t code = 0;
+	uint32_t hits = 0;
+	for (uint32_t j = 0; j < len; ++j) {
+		code = ((code << ix.symBits) | sym_of(tc[b + j], ix.symTable, ix.A)) & mask;
+		if (j + 1 >= (uint32_t)ix.g)
+			for (uint32_t i = 0; i < nGrams; ++i)
+				if (qcode[i] == code) hits |= 1u << i;
+	}
+	return __popc(hits);
+}
+
+// ---------------------------------------------------------------------------------------------- query prep
+template <class U>
+__global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __restrict__ qchars, const uint32_t* __restrict__ qoff,
+                                                    uint32_t nq, float threshold, uint32_t limit, U* __restrict__ qnorm,
+                                                    QDesc* __restrict__ desc, uint32_t* __restrict__ fastList,
+                                                    uint32_t* __restrict__ denseList, uint32_t* __restrict__ counters,
+                                                    uint32_t* __restrict__ outCount)
+{
+	const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (q >= nq) return;
+	QDesc& d = desc[q];
+	uint32_t b = qoff[q], e = qoff[q + 1];
+	const uint32_t g = ix.g;
+	// wildcard: raw query "" or "*" (hpp:356)
+	const bool wildcard = (e == b) || (e - b == 1 && qchars[b] == (U)'*');
+	// trim after escapeBlank (hpp:372-373)
+	uint32_t tb = b, te = e;
+	if (!wildcard) {
+		while (tb < te && unit_blank(qchars[tb], ix.validLut)) ++tb;
+		while (te > tb && unit_blank(qchars[te - 1], ix.validLut)) --te;
+	}
+	const uint32_t qlen = wildcard ? 0 : te - tb;
+	for (uint32_t j = lane; j < qlen; j += 32) qnorm[b + j] = unit_norm(qchars[tb + j], ix.validLut);   // toUpper (hpp:376)
+	__syncwarp();
+	const uint32_t nGrams = qlen >= g ? qlen - g + 1 : 0;
+	uint32_t cls;
+	const bool shortActive = qlen < 3 * g && (ix.nShort > 0 || qlen <= g);           // hpp:381, 240-253
+	if (wildcard) cls = QC_WILDCARD;
+	else if (qlen == 0) cls = QC_EMPTY;                                               // hpp:374-375
+	else if (!shortActive && nGrams >= 1 && nGrams <= MAX_QGRAMS && limit <= FAST_KLIM) cls = QC_FAST;
+	else cls = QC_DENSE;
+
+	uint32_t nLists = 0, total = 0;
+	if (cls == QC_FAST || (cls == QC_DENSE && nGrams >= 1 && nGrams <= MAX_QGRAMS)) {
+		// lane i owns window i
+		const bool act = (uint32_t)lane < nGrams;
+		uint64_t code = ~0ull;
+		if (act) {
+			code = 0;
+			bool ok = true;
+			for (uint32_t j = 0; j < g; ++j) {
+				uint32_t sy = sym_of(qnorm[b + lane + j], ix.symTable, ix.A);
+				ok &= sy != 0;
+				code = (code << ix.symBits) | sy;
+			}
+			if (!ok) code = ~0ull;
+		}
+		d.qcode[lane] = code;
+		// duplicates: one list per distinct gram, multiplicity = number of windows (hpp:289-298 adds once per window)
+		unsigned peers = __match_any_sync(0xffffffffu, code);
+		const bool leader = act && code != ~0ull && (peers & ((1u << lane) - 1)) == 0;
+		uint32_t lo = 0, len = 0;
+		if (leader) {
+			uint32_t a = 0, z = ix.G;
+			while (a < z) { uint32_t m = (a + z) >> 1; if (ix.gramCodes[m] < code) a = m + 1; else z = m; }
+			if (a < ix.G && ix.gramCodes[a] == code) { lo = ix.gramOff[a]; len = ix.gramOff[a + 1] - lo; }
+		}
+		unsigned found = __ballot_sync(0xffffffffu, leader && len > 0);
+		if (leader && len > 0) {
+			uint32_t slot = __popc(found & ((1u << lane) - 1));
+			d.listOff[slot] = lo; d.listLen[slot] = len; d.listMult[slot] = (uint8_t)__popc(peers);
+		}
+		nLists = __popc(found);
+		total = len;
+		for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+	}
+	if (lane == 0) {
+		uint32_t cmin = nGrams + 1, cprom = nGrams + 1;
+		for (uint32_t c = nGrams; c >= 1; --c) {
+			float s = term_score(c, nGrams);
+			if (!(s < threshold)) cmin = c;                                           // hpp:315
+			if ((double)s > 0.999) cprom = c;                                         // hpp:328
+		}
+		d.cls = cls; d.qlen = qlen; d.nGrams = nGrams; d.nLists = nLists; d.cmin = cmin; d.cprom = cprom; d.total = total; d.qbeg = b;
+		outCount[q] = 0;
+		if (cls == QC_FAST) fastList[atomicAdd(&counters[0], 1u)] = q;
+		else if (cls == QC_DENSE || cls == QC_WILDCARD) denseList[atomicAdd(&counters[1], 1u)] = q;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- fast path
+struct FastShared {
+	uint32_t win[FS_WIN_ALLOC];
+	unsigned long long buf[FS_BUF];
+	uint32_t hist[256];
+	uint32_t cur[MAX_QGRAMS], rem[MAX_QGRAMS], nTake[MAX_QGRAMS], mult[MAX_QGRAMS];
+	const uint32_t* base[MAX_QGRAMS];
+	uint64_t qcode[MAX_QGRAMS];
+	uint32_t hiKey[MAX_QGRAMS + 1];    // ~ordered(value) of a weight-1 (or upper-bound) candidate with count c
+	float sOf[MAX_QGRAMS + 1];         // term score for count c
+	unsigned long long tau;
+	uint32_t bufCount, overflow, stride, bound, longest, nActive, query, selPrefixHi, selPrefixLo, selK;
+};
+
+__device__ __forceinline__ uint32_t lower_bound_smem(const uint32_t* a, uint32_t n, uint32_t x)
+{
+	uint32_t lo = 0, hi = n;
+	while (lo < hi) {
+		uint32_t mid = (lo + hi) >> 1;
+		if (a[mid] < x) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+
+// keeps the k smallest entries of buf[0..n) (all distinct), returns the k-th smallest as the new tau. CTA-wide.
+__device__ void select_smallest(FastShared& sh, uint32_t n, uint32_t k)
+{
+	const int tid = threadIdx.x;
+	unsigned long long prefix = 0;
+	uint32_t kk = k;
+	for (int shift = 56; shift >= 0; shift -= 8) {
+		sh.hist[tid] = 0;
+		__syncthreads();
+		for (uint32_t i = tid; i < n; i += FS_THREADS) {
+			unsigned long long v = sh.buf[i];
+			if (shift == 56 || (v >> (shift + 8)) == prefix) atomicAdd(&sh.hist[(uint32_t)(v >> shift) & 255u], 1u);
+		}
+		__syncthreads();
+		if (tid < 32) {
+			// warp scan over 256 bins: lane owns 8 consecutive bins
+			uint32_t loc[8], sum = 0;
+#pragma unroll
+			for (int j = 0; j < 8; ++j) { loc[j] = sh.hist[tid * 8 + j]; sum += loc[j]; }
+			uint32_t inc = sum;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
+			uint32_t exc = inc - sum;
+			if (kk > exc && kk <= inc) {
+				uint32_t run = exc;
+#pragma unroll
+				for (int j = 0; j < 8; ++j) {
+					if (kk > run && kk <= run + loc[j]) { sh.selPrefixLo = tid * 8 + j; sh.selK = kk - run; }
+					run += loc[j];
+				}
+			}
+		}
+		__syncthreads();
+		prefix = (prefix << 8) | sh.selPrefixLo;
+		kk = sh.selK;
+	}
+	// prefix is now the k-th smallest value; compact entries <= prefix to the front
+	unsigned long long keep[FS_BUF / FS_THREADS];
+	uint32_t nk = 0;
+	for (uint32_t i = tid; i < n; i += FS_THREADS) {
+		unsigned long long v = sh.buf[i];
+		if (v <= prefix) keep[nk++] = v;
+	}
+	if (tid == 0) { sh.bufCount = 0; sh.tau = prefix; }
+	__syncthreads();
+	for (uint32_t j = 0; j < nk; ++j) sh.buf[atomicAdd(&sh.bufCount, 1u)] = keep[j];
+	__syncthreads();
+}
+
+// ascending bitonic sort of buf[0..n), n <= FS_BUF. CTA-wide.
+__device__ void sort_buffer(FastShared& sh, uint32_t n)
+{
+	uint32_t p = 1;
+	while (p < n) p <<= 1;
+	for (uint32_t i = n + threadIdx.x; i < p; i += FS_THREADS) sh.buf[i] = ~0ull;
+	__syncthreads();
+	for (uint32_t size = 2; size <= p; size <<= 1)
+		for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+			for (uint32_t i = threadIdx.x; i < (p >> 1); i += FS_THREADS) {
+				uint32_t lo = 2 * i - (i & (stride - 1));
+				uint32_t hi = lo + stride;
+				bool up = (lo & size) == 0;
+				unsigned long long a = sh.buf[lo], b = sh.buf[hi];
+				if ((a > b) == up) { sh.buf[lo] = b; sh.buf[hi] = a; }
+			}
+			__syncthreads();
+		}
+}
+
+template <class U, int KT>
+__device__ __forceinline__ void merge_pass(const IndexView& ix, FastShared& sh, const QDesc& d, const U* __restrict__ qn, uint32_t nLists)
+{
+	const int tid = threadIdx.x;
+	const uint32_t stride = sh.stride;
+	const uint32_t j = sh.longest, nj = sh.nTake[j];
+	const uint32_t a0 = (uint32_t)(((unsigned long long)tid * nj) / FS_THREADS);
+	const uint32_t a1 = (uint32_t)(((unsigned long long)(tid + 1) * nj) / FS_THREADS);
+	const uint32_t lo = tid == 0 ? 0u : sh.win[j * stride + a0];
+	const uint32_t hi = (tid == FS_THREADS - 1) ? INF : sh.win[j * stride + a1];
+	if (lo >= hi) return;
+	uint32_t pos[KT], head[KT];
+#pragma unroll
+	for (int i = 0; i < KT; ++i) {
+		if ((uint32_t)i < nLists) {
+			const uint32_t* w = sh.win + i * stride;
+			pos[i] = i * stride + (tid == 0 ? 0u : lower_bound_smem(w, sh.nTake[i], lo));
+		} else pos[i] = FS_WIN_ALLOC - 1;          // shared INF slot
+		head[i] = sh.win[pos[i]];
+	}
+	const unsigned long long tau = sh.tau;
+	const uint32_t cmin = d.cmin, cprom = d.cprom, nGrams = d.nGrams;
+	while (true) {
+		uint32_t m = head[0];
+#pragma unroll
+		for (int i = 1; i < KT; ++i) m = min(m, head[i]);
+		if (m >= hi) break;
+		uint32_t c = 0;
+#pragma unroll
+		for (int i = 0; i < KT; ++i) {
+			const bool eq = head[i] == m;
+			c += eq ? sh.mult[i] : 0u;
+			pos[i] += eq;
+			if (eq) head[i] = sh.win[pos[i]];
+		}
+		if (c < cmin) continue;                                             // s_t < threshold (hpp:315)
+		// cheap bound: even the best possible value of this term cannot beat the running k-th best
+		if ((((unsigned long long)sh.hiKey[c]) << 32) >= tau) continue;
+		const float s = sh.sOf[c];
+		if (ix.identity && ix.uniformW) {
+			const uint32_t kid = m;
+			uint32_t hk = sh.hiKey[c];
+			if (c >= cprom && key_equals_query<U>(ix, kid, qn, d.qlen)) hk = ~float_to_ordered(100.0f);   // hpp:333-335
+			const unsigned long long key = ((unsigned long long)hk << 32) | kid;
+			if (key < tau) {
+				uint32_t idx = atomicAdd(&sh.bufCount, 1u);
+				if (idx < FS_BUF) sh.buf[idx] = key; else sh.overflow = 1;
+			}
+		} else {
+			for (uint32_t e = ix.termEdgeOff[m]; e < ix.termEdgeOff[m + 1]; ++e) {       // hpp:321-338
+				const uint32_t kid = ix.edgeKid[e];
+				float v = edge_value(ix.edgeW[e], s);
+				const bool prom = c >= cprom && key_equals_query<U>(ix, kid, qn, d.qlen);
+				if (prom) v = 100.0f;
+				const unsigned long long key = rank_key(v, kid);
+				if (key >= tau) continue;
+				// a key reachable through several terms is emitted once, by the edge with the best value
+				// (per-key max-merge, hpp:326; ties -> smallest term id)
+				bool dominated = false;
+				const uint32_t kb = ix.keyEdgeOff[kid], ke = ix.keyEdgeOff[kid + 1];
+				for (uint32_t x = kb; x < ke && ke - kb > 1 && !dominated; ++x) {
+					const uint32_t t2 = ix.keyEdgeTerm[x];
+					if (t2 == m) continue;
+					const uint32_t c2 = count_for_term<U>(ix, t2, sh.qcode, nGrams);
+					if (c2 < cmin || c2 == 0) continue;
+					float v2 = edge_value(ix.keyEdgeW[x], sh.sOf[c2]);
+					if (c2 >= cprom && (prom || key_equals_query<U>(ix, kid, qn, d.qlen))) v2 = 100.0f;
+					dominated = v2 > v || (v2 == v && t2 < m);
+				}
+				if (dominated) continue;
+				uint32_t idx = atomicAdd(&sh.bufCount, 1u);
+				if (idx < FS_BUF) sh.buf[idx] = key; else sh.overflow = 1;
+			}
+		}
+	}
+}
+
+template <class U>
+__global__ void __launch_bounds__(FS_THREADS) k_fast_search(IndexView ix, const QDesc* __restrict__ desc, const U* __restrict__ qnorm,
+                                                            const uint32_t* __restrict__ fastList, uint32_t* __restrict__ counters,
+                                                            uint32_t* __restrict__ denseList, uint32_t limit, uint32_t outStride,
+                                                            uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
+                                                            float* __restrict__ outScore, unsigned long long* __restrict__ statCounters)
+{
+	extern __shared__ __align__(16) unsigned char fs_smem[];
+	FastShared& sh = *reinterpret_cast<FastShared*>(fs_smem);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t nFast = counters[0];
+	if (tid == 0) sh.win[FS_WIN_ALLOC - 1] = INF;
+
+	while (true) {
+		__syncthreads();
+		if (tid == 0) sh.query = atomicAdd(&counters[2], 1u);
+		__syncthreads();
+		const uint32_t wi = sh.query;
+		if (wi >= nFast) break;
+		const uint32_t q = fastList[wi];
+		const QDesc& d = desc[q];
+		const U* qn = qnorm + d.qbeg;
+		const uint32_t nLists = d.nLists, nGrams = d.nGrams;
+		const uint32_t k = limit;
+		if (tid < MAX_QGRAMS) {
+			sh.qcode[tid] = (uint32_t)tid < nGrams ? d.qcode[tid] : ~0ull;
+			if ((uint32_t)tid < nLists) {
+				sh.base[tid] = ix.postings + d.listOff[tid];
+				sh.cur[tid] = 0; sh.rem[tid] = d.listLen[tid]; sh.mult[tid] = d.listMult[tid];
+			} else { sh.rem[tid] = 0; sh.mult[tid] = 0; sh.nTake[tid] = 0; }
+		}
+		if (tid <= MAX_QGRAMS) {
+			const uint32_t c = tid;
+			float s = (c <= nGrams && nGrams) ? term_score(c, nGrams) : 0.0f;
+			sh.sOf[c] = s;
+			// identity/uniform: the exact value (weight 1); otherwise an upper bound over all edges of any term
+			float ub = ix.uniformW ? edge_value(1.0f, s) : edge_value(ix.wmax, s);
+			if (c >= d.cprom) ub = fmaxf(ub, 100.0f);
+			sh.hiKey[c] = ~float_to_ordered(ub);
+		}
+		if (tid == 0) { sh.bufCount = 0; sh.overflow = 0; sh.tau = ~0ull; }
+		__syncthreads();
+
+		bool firstPass = true, failed = false, safeMode = false;
+		uint32_t level = 0;
+		while (true) {
+			// ---- plan the pass
+			uint32_t nAct = 0;
+			for (uint32_t i = 0; i < nLists; ++i) nAct += sh.rem[i] > 0;
+			if (nAct == 0) break;
+			uint32_t cap = FS_WIN;
+			if (firstPass && d.total > FS_FIRST_PASS) cap = FS_FIRST_PASS;
+			if (safeMode) cap = min(cap, (uint32_t)FS_BUF - level);
+			const uint32_t wmax = max(1u, cap / nLists);        // regions are laid out for all lists (exhausted ones stay empty)
+			const uint32_t stride = wmax + 1;
+			// ---- stage windows (coalesced)
+			for (uint32_t i = 0; i < nLists; ++i) {
+				const uint32_t take = min(sh.rem[i], stride);
+				const uint32_t* src = sh.base[i] + sh.cur[i];
+				uint32_t* dst = sh.win + i * stride;
+				for (uint32_t x = tid; x < take; x += FS_THREADS) dst[x] = __ldg(src + x);
+			}
+			__syncthreads();
+			// ---- pass bound b = min over lists of the first element NOT covered; consumed counts; sentinels
+			if (warp == 0) {
+				uint32_t bound = INF;
+				if ((uint32_t)lane < nLists && sh.rem[lane] > wmax) bound = sh.win[lane * stride + wmax];
+				for (int o = 16; o; o >>= 1) bound = min(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+				uint32_t nt = 0;
+				if ((uint32_t)lane < nLists) {
+					const uint32_t avail = min(sh.rem[lane], wmax);
+					nt = bound == INF ? avail : lower_bound_smem(sh.win + lane * stride, avail, bound);
+					sh.nTake[lane] = nt;
+					sh.win[lane * stride + nt] = INF;
+				}
+				uint32_t best = nt, bi = lane;
+				for (int o = 16; o; o >>= 1) {
+					uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+					if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+				}
+				if (lane == 0) { sh.stride = stride; sh.longest = bi; }
+			}
+			__syncthreads();
+			// ---- merge
+			if (nLists <= 4) merge_pass<U, 4>(ix, sh, d, qn, nLists);
+			else if (nLists <= 8) merge_pass<U, 8>(ix, sh, d, qn, nLists);
+			else if (nLists <= 12) merge_pass<U, 12>(ix, sh, d, qn, nLists);
+			else if (nLists <= 16) merge_pass<U, 16>(ix, sh, d, qn, nLists);
+			else if (nLists <= 24) merge_pass<U, 24>(ix, sh, d, qn, nLists);
+			else merge_pass<U, 32>(ix, sh, d, qn, nLists);
+			__syncthreads();
+			if (sh.overflow) {
+				// the optimistic pass overflowed the candidate buffer: roll it back, make room, redo it with a
+				// window small enough to be safe for single-edge terms; if even that overflows -> dense path
+				if (safeMode && level <= k) { failed = true; break; }
+				__syncthreads();
+				if (tid == 0) { sh.bufCount = level; sh.overflow = 0; }
+				__syncthreads();
+				if (level > k) { select_smallest(sh, level, k); level = k; }
+				safeMode = true;
+				continue;
+			}
+			safeMode = false;
+			firstPass = false;
+			if (tid < MAX_QGRAMS && (uint32_t)tid < nLists) { sh.cur[tid] += sh.nTake[tid]; sh.rem[tid] -= sh.nTake[tid]; }
+			level = sh.bufCount;
+			__syncthreads();
+			// establish / tighten tau once enough candidates are buffered
+			if (level > k && (sh.tau == ~0ull || level > FS_BUF / 2)) { select_smallest(sh, level, k); level = k; }
+		}
+		if (failed) {
+			if (tid == 0) {
+				denseList[atomicAdd(&counters[1], 1u)] = q;
+				atomicAdd(&counters[3], 1u);
+			}
+			continue;
+		}
+		// ---- final: top-k, sorted
+		if (level > k) { select_smallest(sh, level, k); level = k; }
+		sort_buffer(sh, level);
+		for (uint32_t i = tid; i < level; i += FS_THREADS) {
+			unsigned long long v = sh.buf[i];
+			outKid[(size_t)q * outStride + i] = (uint32_t)v;
+			outScore[(size_t)q * outStride + i] = rank_key_score(v);
+		}
+		if (tid == 0) {
+			outCount[q] = level;
+			atomicAdd(&statCounters[0], (unsigned long long)d.total);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- dense path
+// one CTA per gram window of the query: counts[t] += 1 for every term of the window's posting list (hpp:289-298)
+template <class U>
+__global__ void __launch_bounds__(256) k_dense_count(IndexView ix, const U* __restrict__ qn, uint32_t qlen, uint32_t* __restrict__ cnt)
+{
+	__shared__ uint32_t sLo, sLen;
+	const uint32_t w = blockIdx.x;
+	if (threadIdx.x == 0) {
+		uint64_t code = 0;
+		bool ok = true;
+		for (int j = 0; j < ix.g; ++j) {
+			uint32_t sy = sym_of(qn[w + j], ix.symTable, ix.A);
+			ok &= sy != 0;
+			code = (code << ix.symBits) | sy;
+		}
+		uint32_t lo = 0, len = 0;
+		if (ok) {
+			uint32_t a = 0, z = ix.G;
+			while (a < z) { uint32_t m = (a + z) >> 1; if (ix.gramCodes[m] < code) a = m + 1; else z = m; }
+			if (a < ix.G && ix.gramCodes[a] == code) { lo = ix.gramOff[a]; len = ix.gramOff[a + 1] - lo; }
+		}
+		sLo = lo; sLen = len;
+	}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < sLen; i += blockDim.x) atomicAdd(&cnt[ix.postings[sLo + i]], 1u);
+	(void)qlen;
+}
+
+// per-key max-merge: entry[kid] = max(entry[kid], value) on order-preserving bits; 0 = key absent
+template <class U>
+__device__ __forceinline__ void dense_apply_term(const IndexView& ix, uint32_t t, float s, float threshold, const U* __restrict__ qn,
+                                                 uint32_t qlen, uint32_t* __restrict__ entry)
+{
+	if (s < threshold) return;                                                        // hpp:315
+	const bool perfect = (double)s > 0.999;                                           // hpp:328
+	for (uint32_t e = ix.termEdgeOff[t]; e < ix.termEdgeOff[t + 1]; ++e) {
+		const uint32_t kid = ix.edgeKid[e];
+		float v = edge_value(ix.edgeW[e], s);
+		if (perfect && key_equals_query<U>(ix, kid, qn, qlen)) v = 100.0f;
+		atomicMax(&entry[kid], float_to_ordered(v));
+	}
+}
+template <class U>
+__global__ void __launch_bounds__(256) k_dense_long(IndexView ix, const uint32_t* __restrict__ cnt, uint32_t nGrams, float threshold,
+                                                    const U* __restrict__ qn, uint32_t qlen, uint32_t* __restrict__ entry)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= ix.T) return;
+	uint32_t c = cnt[t];
+	if (c) dense_apply_term<U>(ix, t, term_score(c, nGrams), threshold, qn, qlen, entry);
+}
+// stringMatch (hpp:182-222) restated column-wise: semi-global edit distance, free start and end in the source
+template <class U>
+__device__ uint32_t string_match(const U* __restrict__ q, uint32_t nq, const U* __restrict__ s, uint32_t ns)
+{
+	if (nq == 1) {
+		for (uint32_t j = 0; j < ns; ++j) if (s[j] == q[0]) return 1;
+		return 0;
+	}
+	uint32_t col[3 * MAX_GSIZE + 1];
+	for (uint32_t a = 0; a <= nq; ++a) col[a] = a;
+	uint32_t best = col[nq];
+	for (uint32_t j = 0; j < ns; ++j) {
+		uint32_t diag = col[0];          // D[a][j]
+		const U sc = s[j];
+		for (uint32_t a = 0; a < nq; ++a) {
+			uint32_t up = col[a + 1];    // D[a+1][j]
+			uint32_t v = min(min(col[a] + 1, up + 1), diag + (q[a] != sc ? 1u : 0u));
+			diag = up;
+			col[a + 1] = v;
+		}
+		best = min(best, col[nq]);
+	}
+	return nq - best;
+}
+// short path (hpp:232-254): every short term, and every long term too when |q| <= gSize
+template <class U>
+__global__ void __launch_bounds__(256) k_dense_short(IndexView ix, uint32_t nScan, int allTerms, float threshold, const U* __restrict__ qn,
+                                                     uint32_t qlen, uint32_t* __restrict__ entry)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nScan) return;
+	uint32_t t;
+	if (allTerms) {
+		t = i;
+		if (ix.termOff[t + 1] - ix.termOff[t] < 2u * ix.g) return;      // short terms are handled by the other launch
+	} else t = ix.shortTerms[i];
+	const U* tc = reinterpret_cast<const U*>(ix.termChars) + ix.termOff[t];
+	uint32_t m = string_match<U>(qn, qlen, tc, ix.termOff[t + 1] - ix.termOff[t]);
+	dense_apply_term<U>(ix, t, __fdiv_rn((float)m, (float)qlen), threshold, qn, qlen, entry);   // hpp:244
+}
+__global__ void k_dense_wildcard(IndexView ix, uint32_t* __restrict__ entry)
+{
+	uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= ix.K) return;
+	if (ix.keyEdgeOff[k + 1] > ix.keyEdgeOff[k]) entry[k] = float_to_ordered(ix.keyWmax[k]);   // hpp:358-368
+}
+__global__ void k_dense_flags(const uint32_t* __restrict__ entry, uint32_t K, uint8_t* __restrict__ flag)
+{
+	uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < K) flag[k] = entry[k] != 0;
+}
+__global__ void k_dense_collect(const uint32_t* __restrict__ entry, const uint8_t* __restrict__ flag, const uint32_t* __restrict__ pos,
+                                uint32_t K, uint64_t* __restrict__ keys)
+{
+	uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < K && flag[k]) keys[pos[k]] = ((uint64_t)(~entry[k]) << 32) | k;
+}
+__global__ void k_dense_emit(const uint64_t* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ kid, float* __restrict__ score)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) { kid[i] = (uint32_t)sorted[i]; score[i] = rank_key_score(sorted[i]); }
+}
+
+inline unsigned grid_for(size_t n, int tpb = 256) { return (unsigned)std::max<size_t>(1, (n + tpb - 1) / tpb); }
+
+template <class U>
+void run_dense_query(const DeviceIndex& ix, const IndexView& v, SearchWorkspace& ws, const QDesc& d, uint32_t q, float threshold,
+                     uint32_t limit, uint32_t stride, BatchOutput* out, cudaStream_t s)
+{
+	const U* qn = reinterpret_cast<const U*>(ws.qnorm.get()) + d.qbeg;
+	ws.entry.reserve(std::max(ix.K, 1u), s);
+	SSB_CUDA(cudaMemsetAsync(ws.entry.get(), 0, (size_t)ix.K * sizeof(uint32_t), s));
+	if (d.cls == QC_WILDCARD) {
+		k_dense_wildcard<<<grid_for(ix.K), 256, 0, s>>>(v, ws.entry.get());
+		SSB_LAUNCH_CHECK();
+	} else {
+		const uint32_t g = ix.g;
+		if (d.qlen < 3 * g) {                                                           // hpp:381
+			if (ix.nShort) {
+				k_dense_short<U><<<grid_for(ix.nShort), 256, 0, s>>>(v, ix.nShort, 0, threshold, qn, d.qlen, ws.entry.get());
+				SSB_LAUNCH_CHECK();
+			}
+			if (d.qlen <= g) {                                                          // hpp:247
+				k_dense_short<U><<<grid_for(ix.T), 256, 0, s>>>(v, ix.T, 1, threshold, qn, d.qlen, ws.entry.get());
+				SSB_LAUNCH_CHECK();
+			}
+		}
+		if (d.nGrams >= 1 && ix.P) {                                                    // hpp:281
+			ws.cnt.reserve(ix.T, s);
+			SSB_CUDA(cudaMemsetAsync(ws.cnt.get(), 0, (size_t)ix.T * sizeof(uint32_t), s));
+			k_dense_count<U><<<d.nGrams, 256, 0, s>>>(v, qn, d.qlen, ws.cnt.get());
+			SSB_LAUNCH_CHECK();
+			k_dense_long<U><<<grid_for(ix.T), 256, 0, s>>>(v, ws.cnt.get(), d.nGrams, threshold, qn, d.qlen, ws.entry.get());
+			SSB_LAUNCH_CHECK();
+		}
+	}
+	// collect present keys, sort by rank key, keep the first `limit`
+	DevBuf<uint8_t> flag(ix.K, s);
+	DevBuf<uint32_t> pos(ix.K, s), dN(1, s);
+	k_dense_flags<<<grid_for(ix.K), 256, 0, s>>>(ws.entry.get(), ix.K, flag.get());
+	SSB_LAUNCH_CHECK();
+	exclusive_scan_u8_u32(flag.get(), pos.get(), ix.K, dN.get(), s);
+	uint32_t n = 0;
+	SSB_CUDA(cudaMemcpyAsync(&n, dN.get(), 4, cudaMemcpyDeviceToHost, s));
+	SSB_CUDA(cudaStreamSynchronize(s));
+	uint32_t take = std::min(n, limit);
+	if (n) {
+		DevBuf<uint64_t> k1(n, s), k2(n, s);
+		k_dense_collect<<<grid_for(ix.K), 256, 0, s>>>(ws.entry.get(), flag.get(), pos.get(), ix.K, k1.get());
+		SSB_LAUNCH_CHECK();
+		int kidBits = 1;
+		while ((1ull << kidBits) < ix.K) ++kidBits;
+		bool a1 = radix_sort_u64(k1.get(), k2.get(), nullptr, nullptr, n, 0, kidBits, s);
+		uint64_t *ka = a1 ? k2.get() : k1.get(), *kb = a1 ? k1.get() : k2.get();
+		bool a2 = radix_sort_u64(ka, kb, nullptr, nullptr, n, 32, 64, s);
+		const uint64_t* sorted = a2 ? kb : ka;
+		if (take <= stride) {
+			k_dense_emit<<<grid_for(take), 256, 0, s>>>(sorted, take, ws.outKid.get() + (size_t)q * stride,
+			                                           ws.outScore.get() + (size_t)q * stride);
+			SSB_LAUNCH_CHECK();
+			SSB_CUDA(cudaMemcpyAsync(ws.outCount.get() + q, &take, 4, cudaMemcpyHostToDevice, s));
+			SSB_CUDA(cudaStreamSynchronize(s));   // `take` lives on this stack frame
+		} else if (out) {
+			DevBuf<uint32_t> dk(take, s);
+			DevBuf<float> dsc(take, s);
+			k_dense_emit<<<grid_for(take), 256, 0, s>>>(sorted, take, dk.get(), dsc.get());
+			SSB_LAUNCH_CHECK();
+			std::vector<uint32_t> hkid(take);
+			std::vector<float> hsc(take);
+			SSB_CUDA(cudaMemcpyAsync(hkid.data(), dk.get(), (size_t)take * 4, cudaMemcpyDeviceToHost, s));
+			SSB_CUDA(cudaMemcpyAsync(hsc.data(), dsc.get(), (size_t)take * 4, cudaMemcpyDeviceToHost, s));
+			uint32_t marker = 0xFFFFFFFFu;
+			SSB_CUDA(cudaMemcpyAsync(ws.outCount.get() + q, &marker, 4, cudaMemcpyHostToDevice, s));
+			SSB_CUDA(cudaStreamSynchronize(s));
+			std::vector<std::pair<uint32_t, float>> lst(take);
+			for (uint32_t i = 0; i < take; ++i) lst[i] = {hkid[i], hsc[i]};
+			out->big.emplace_back(q, std::move(lst));
+		}
+	} else {
+		uint32_t zero = 0;
+		SSB_CUDA(cudaMemcpyAsync(ws.outCount.get() + q, &zero, 4, cudaMemcpyHostToDevice, s));
+		SSB_CUDA(cudaStreamSynchronize(s));
+	}
+}
+
+void ensure_workspace(SearchWorkspace& ws, uint32_t nq, size_t charBytes, uint32_t stride, cudaStream_t s)
+{
+	if (!ws.ev0) {
+		SSB_CUDA(cudaEventCreate(&ws.ev0)); SSB_CUDA(cudaEventCreate(&ws.ev1));
+		SSB_CUDA(cudaEventCreate(&ws.ev2)); SSB_CUDA(cudaEventCreate(&ws.ev3));
+		ws.counters.alloc(8, s);
+		ws.statCounters.alloc(4, s);
+	}
+	if (nq > ws.capQ || stride > ws.stride) {
+		uint32_t cq = std::max(nq, ws.capQ), st = std::max(stride, ws.stride);
+		ws.qoff.alloc(cq + 1, s); ws.desc.alloc(cq, s); ws.fastList.alloc(cq, s); ws.denseList.alloc(cq, s);
+		ws.outCount.alloc(cq, s); ws.outKid.alloc((size_t)cq * st, s); ws.outScore.alloc((size_t)cq * st, s);
+		ws.capQ = cq; ws.stride = st;
+	}
+	if (charBytes > ws.capChars) {
+		ws.capChars = charBytes + charBytes / 4 + 64;
+		ws.qchars.alloc(ws.capChars, s); ws.qnorm.alloc(ws.capChars, s);
+	}
+}
+
+template <class U>
+void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float threshold, uint32_t limit, uint32_t stride,
+                BatchOutput* out, cudaStream_t s, SearchStats* st)
+{
+	const IndexView v = make_view(ix);
+	static int numSMs = 0, ctasPerSM = 1;
+	static size_t smemBytes = sizeof(FastShared);
+	if (!numSMs) {
+		int dev = 0;
+		SSB_CUDA(cudaGetDevice(&dev));
+		SSB_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
+		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_fast_search<U>, FS_THREADS, smemBytes));
+		if (ctasPerSM < 1) ctasPerSM = 1;
+	}
+	SSB_CUDA(cudaEventRecord(ws.ev0, s));
+	ws.counters.zero(s);
+	ws.statCounters.zero(s);
+	const U* qc = reinterpret_cast<const U*>(ws.qchars.get());
+	U* qn = reinterpret_cast<U*>(ws.qnorm.get());
+	k_query_prep<U><<<grid_for((size_t)nq * 32), 256, 0, s>>>(v, qc, ws.qoff.get(), nq, threshold, limit, qn, ws.desc.get(),
+	                                                          ws.fastList.get(), ws.denseList.get(), ws.counters.get(),
+	                                                          ws.outCount.get());
+	SSB_LAUNCH_CHECK();
+	SSB_CUDA(cudaEventRecord(ws.ev1, s));
+	// persistent grid: one wave of resident CTAs (148 SMs x occupancy), queries handed out by an atomic cursor
+	const unsigned grid = (unsigned)std::min<size_t>((size_t)numSMs * ctasPerSM, std::max<uint32_t>(nq, 1));
+	k_fast_search<U><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(), ws.denseList.get(),
+	                                                     limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(),
+	                                                     ws.statCounters.get());
+	SSB_LAUNCH_CHECK();
+	SSB_CUDA(cudaEventRecord(ws.ev2, s));
+	uint32_t hc[4];
+	SSB_CUDA(cudaMemcpyAsync(hc, ws.counters.get(), sizeof hc, cudaMemcpyDeviceToHost, s));
+	SSB_CUDA(cudaStreamSynchronize(s));
+	const uint32_t nDense = hc[1];
+	if (nDense) {
+		std::vector<uint32_t> dl(nDense);
+		SSB_CUDA(cudaMemcpyAsync(dl.data(), ws.denseList.get(), (size_t)nDense * 4, cudaMemcpyDeviceToHost, s));
+		SSB_CUDA(cudaStreamSynchronize(s));
+		std::sort(dl.begin(), dl.end());
+		for (uint32_t q : dl) {
+			QDesc d;
+			SSB_CUDA(cudaMemcpyAsync(&d, ws.desc.get() + q, sizeof(QDesc), cudaMemcpyDeviceToHost, s));
+			SSB_CUDA(cudaStreamSynchronize(s));
+			run_dense_query<U>(ix, v, ws, d, q, threshold, limit, stride, out, s);
+		}
+	}
+	SSB_CUDA(cudaEventRecord(ws.ev3, s));
+	SSB_CUDA(cudaEventSynchronize(ws.ev3));
+	if (st) {
+		unsigned long long sc[2];
+		SSB_CUDA(cudaMemcpy(sc, ws.statCounters.get(), sizeof sc, cudaMemcpyDeviceToHost));
+		st->nFast = hc[0]; st->nDense = nDense; st->nOverflow = hc[3];
+		st->postingsTouched = sc[0];
+		SSB_CUDA(cudaEventElapsedTime(&st->msDevice, ws.ev0, ws.ev3));
+		SSB_CUDA(cudaEventElapsedTime(&st->msFastKernel, ws.ev1, ws.ev2));
+	}
+}
+
+}   // namespace
+
+void search_batch(const DeviceIndex& ix, SearchWorkspace& ws, const void* qchars, const uint32_t* qoff, uint32_t nq, float threshold,
+                  uint32_t limit, BatchOutput& out, cudaStream_t s, SearchStats* stats)
+{
+	out = BatchOutput();
+	out.nq = nq;
+	if (limit == 0) limit = 0x7FFFFFFFu;                                               // hpp:420-421,454-455
+	const uint32_t stride = std::min<uint32_t>(limit, FAST_KLIM);
+	out.stride = stride;
+	out.count.assign(nq, 0);
+	if (!ix.indexed || nq == 0) return;                                                // hpp:417,451
+	const size_t charBytes = (size_t)qoff[nq] * ix.unit;
+	ensure_workspace(ws, nq, charBytes, stride, s);
+	if (charBytes) SSB_CUDA(cudaMemcpyAsync(ws.qchars.get(), qchars, charBytes, cudaMemcpyHostToDevice, s));
+	SSB_CUDA(cudaMemcpyAsync(ws.qoff.get(), qoff, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
+	if (ix.unit == 1) run_device<uint8_t>(ix, ws, nq, threshold, limit, stride, &out, s, stats);
+	else run_device<uint32_t>(ix, ws, nq, threshold, limit, stride, &out, s, stats);
+	out.kid.resize((size_t)nq * stride);
+	out.score.resize((size_t)nq * stride);
+	SSB_CUDA(cudaMemcpyAsync(out.count.data(), ws.outCount.get(), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+	SSB_CUDA(cudaMemcpyAsync(out.kid.data(), ws.outKid.get(), (size_t)nq * stride * 4, cudaMemcpyDeviceToHost, s));
+	SSB_CUDA(cudaMemcpyAsync(out.score.data(), ws.outScore.get(), (size_t)nq * stride * 4, cudaMemcpyDeviceToHost, s));
+	SSB_CUDA(cudaStreamSynchronize(s));
+	for (auto& b : out.big) out.count[b.first] = (uint32_t)b.second.size();
+}
+
+void search_batch_resident(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float threshold, uint32_t limit, cudaStream_t s,
+                           SearchStats* stats)
+{
+	if (limit == 0) limit = 0x7FFFFFFFu;
+	if (!ix.indexed || nq == 0 || nq > ws.capQ) throw std::runtime_error("search_batch_resident: upload a batch with search_batch first");
+	const uint32_t stride = std::min<uint32_t>(limit, FAST_KLIM);
+	if (stride > ws.stride) throw std::runtime_error("search_batch_resident: limit larger than the uploaded batch's");
+	if (ix.unit == 1) run_device<uint8_t>(ix, ws, nq, threshold, limit, stride, nullptr, s, stats);
+	else run_device<uint32_t>(ix, ws, nq, threshold, limit, stride, nullptr, s, stats);
+}
+
+}   // namespace ssb

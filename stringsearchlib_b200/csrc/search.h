@@ -1,0 +1,87 @@
+// search.h — batched search over a DeviceIndex (replaces StringIndex::_search and its callees,
+// nGramSearch.hpp:182-404).
+#pragma once
+#include "index.h"
+#include <vector>
+
+namespace ssb {
+
+constexpr int MAX_QGRAMS = 32;      // fast path: at most 32 gram windows per query (longer queries take the dense path)
+constexpr int FAST_KLIM = 2048;     // fast path: limit <= FAST_KLIM
+
+enum QueryClass : uint32_t { QC_EMPTY = 0, QC_FAST = 1, QC_DENSE = 2, QC_WILDCARD = 3 };
+
+// per-query descriptor produced by k_query_prep (device) — also read back by the host for dense queries
+struct QDesc {
+	uint32_t cls;
+	uint32_t qlen;        // normalised length in units
+	uint32_t nGrams;      // |Q| = qlen - g + 1 windows, duplicates kept (nGramSearch.hpp:29-36); 0 when qlen < g
+	uint32_t nLists;      // distinct grams present in the index
+	uint32_t cmin;        // smallest count c with !((float)c / (float)nGrams < threshold)   (hpp:315)
+	uint32_t cprom;       // smallest count c with (double)((float)c / (float)nGrams) > 0.999 (hpp:328)
+	uint32_t total;       // postings over all lists
+	uint32_t qbeg;        // offset of the normalised query in the qnorm buffer (units)
+	uint32_t listOff[MAX_QGRAMS];
+	uint32_t listLen[MAX_QGRAMS];
+	uint64_t qcode[MAX_QGRAMS];   // code of every window (dups kept); ~0 = contains a symbol absent from the index
+	uint8_t listMult[MAX_QGRAMS];
+};
+
+struct SearchStats {
+	uint32_t nFast = 0, nDense = 0, nWildcard = 0, nEmpty = 0, nOverflow = 0;
+	uint64_t postingsTouched = 0;   // sum over fast queries of posting-list lengths (algorithmic bytes / 4)
+	uint64_t candidates = 0;
+	float msDevice = 0;             // CUDA-event time of the device part of the last batch
+	float msFastKernel = 0;         // CUDA-event time of k_fast_search alone
+};
+
+// Device + pinned workspace of one index for batched search. Grow-only.
+struct SearchWorkspace {
+	// queries
+	DevBuf<uint8_t> qchars, qnorm;
+	DevBuf<uint32_t> qoff;
+	DevBuf<QDesc> desc;
+	DevBuf<uint32_t> fastList, denseList, counters;   // counters: [0]=nFast [1]=nDense [2]=work cursor [3]=overflow count
+	DevBuf<unsigned long long> statCounters;          // [0]=postings touched [1]=candidates appended
+	// results (fixed stride)
+	DevBuf<uint32_t> outCount, outKid;
+	DevBuf<float> outScore;
+	// dense scratch
+	DevBuf<uint32_t> cnt, entry;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+	uint32_t capQ = 0, stride = 0;
+	size_t capChars = 0;
+	~SearchWorkspace();
+};
+
+struct BatchOutput {
+	uint32_t nq = 0, stride = 0;
+	std::vector<uint32_t> count;          // [nq] results per query
+	std::vector<uint32_t> kid;            // [nq*stride]
+	std::vector<float> score;             // [nq*stride]
+	// queries whose result list did not fit the stride (limit > stride): full lists
+	std::vector<std::pair<uint32_t, std::vector<std::pair<uint32_t, float>>>> big;
+};
+
+// queries: packed units (1 or 4 bytes each as ix.unit) + offsets [nq+1] on the HOST.
+// Runs H2D -> kernels -> D2H. Results are kids (rank ids); HostKeys maps them to strings.
+void search_batch(const DeviceIndex& ix, SearchWorkspace& ws, const void* qchars, const uint32_t* qoff, uint32_t nq, float threshold,
+                  uint32_t limit, BatchOutput& out, cudaStream_t s, SearchStats* stats);
+
+// Device-resident variant used for kernel-only timing: queries must already have been uploaded by a previous
+// search_batch() call with the same arguments; re-runs prep + fast/dense kernels, leaves results on the device.
+void search_batch_resident(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float threshold, uint32_t limit, cudaStream_t s,
+                           SearchStats* stats);
+
+// Multi-shard merge: records of nShards shards -> global top-limit per query (device pointers).
+struct MergeRecord {
+	uint32_t scoreBits;   // IEEE-754 bits of the score
+	uint32_t keyLen;      // key length in units
+	uint64_t row;         // global first row of the key (tie-break: length asc, row asc)
+	uint64_t hash;        // 64-bit hash of the key string (equal strings in different shards collapse, max score wins)
+};
+void export_records(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, uint32_t limit, MergeRecord* d_out, cudaStream_t s);
+void merge_records(const MergeRecord* d_gathered, uint32_t nShards, uint32_t nq, uint32_t limit, MergeRecord* d_out, uint32_t* d_outCount,
+                   cudaStream_t s);
+
+}   // namespace ssb
