@@ -214,7 +214,8 @@ struct FastShared {
 	uint32_t cur[MAX_QGRAMS], rem[MAX_QGRAMS], nTake[MAX_QGRAMS], mult[MAX_QGRAMS];
 	const uint32_t* base[MAX_QGRAMS];
 	uint64_t qcode[MAX_QGRAMS];
-	uint32_t hiKey[MAX_QGRAMS + 1];    // ~ordered(value) of a weight-1 (or upper-bound) candidate with count c
+	uint32_t hiKey[MAX_QGRAMS + 1];    // ~ordered(upper bound of the value of any edge of a term with count c) incl. promotion
+	uint32_t exactKey[MAX_QGRAMS + 1]; // ~ordered(value) of a weight-1, unpromoted candidate with count c
 	float sOf[MAX_QGRAMS + 1];         // term score for count c
 	unsigned long long tau;
 	uint32_t bufCount, overflow, stride, bound, longest, nActive, query, selPrefixHi, selPrefixLo, selK;
@@ -340,7 +341,7 @@ __device__ __forceinline__ void merge_pass(const IndexView& ix, FastShared& sh, 
 		const float s = sh.sOf[c];
 		if (ix.identity && ix.uniformW) {
 			const uint32_t kid = m;
-			uint32_t hk = sh.hiKey[c];
+			uint32_t hk = sh.exactKey[c];
 			if (c >= cprom && key_equals_query<U>(ix, kid, qn, d.qlen)) hk = ~float_to_ordered(100.0f);   // hpp:333-335
 			const unsigned long long key = ((unsigned long long)hk << 32) | kid;
 			if (key < tau) {
@@ -413,6 +414,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_search(IndexView ix, const 
 			sh.sOf[c] = s;
 			// identity/uniform: the exact value (weight 1); otherwise an upper bound over all edges of any term
 			float ub = ix.uniformW ? edge_value(1.0f, s) : edge_value(ix.wmax, s);
+			sh.exactKey[c] = ~float_to_ordered(edge_value(1.0f, s));
 			if (c >= d.cprom) ub = fmaxf(ub, 100.0f);
 			sh.hiKey[c] = ~float_to_ordered(ub);
 		}
@@ -456,9 +458,13 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_search(IndexView ix, const 
 					uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
 					if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
 				}
-				if (lane == 0) { sh.stride = stride; sh.longest = bi; }
+				if (lane == 0) {
+					sh.stride = stride; sh.longest = bi;
+					if (best == 0) sh.overflow = 2;      // no list can advance (corrupt postings): never spin, fall back
+				}
 			}
 			__syncthreads();
+			if (sh.overflow == 2) { failed = true; break; }
 			// ---- merge
 			if (nLists <= 4) merge_pass<U, 4>(ix, sh, d, qn, nLists);
 			else if (nLists <= 8) merge_pass<U, 8>(ix, sh, d, qn, nLists);

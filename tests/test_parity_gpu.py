@@ -1,0 +1,335 @@
+"""Parity tests proper: the CUDA engine, called through its C ABI, against the CPU oracle (oracle/spec) on the same
+seeded inputs — bit-exact tables (keys, terms, edges, gram table, postings) and bit-exact ranked lists + scores — and
+against the reference-generated golden fixture. All tests need a B200 (-m gpu)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from util import assert_same_modulo_ties, random_corpus, spec_keys
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "reference_golden.json")
+
+
+@pytest.fixture(scope="module")
+def ssb():
+    import stringsearchlib_b200 as m
+    return m
+
+
+def check_tables(ix, S):
+    t, o = ix.tables(), S.tables()
+    i = t["info"]
+    assert bool(i["indexed"]) == o["indexed"]
+    for k in ("K", "T", "E", "G", "P", "nShort"):
+        assert i[k] == o[k], (k, i[k], o[k])
+    if i["T"] == 0:
+        return t, o
+    # keys: by kid on the device, by ext id in the oracle
+    ext_of_kid = np.argsort(o["kidOfExt"], kind="stable")
+    lens_o = np.diff(o["keyOffExt"]).astype(np.int64)[ext_of_kid]
+    lens_d = np.diff(t["keyOff"]).astype(np.int64) - 1
+    assert np.array_equal(lens_o, lens_d)
+    chars_o = np.concatenate([o["keyCharsExt"][int(o["keyOffExt"][e]):int(o["keyOffExt"][e + 1])] for e in ext_of_kid]) \
+        if i["K"] < 200000 else None
+    if chars_o is not None:
+        mask = np.ones(len(t["keyChars"]), bool)
+        mask[t["keyOff"][1:].astype(np.int64) - 1] = False          # terminators
+        assert np.all(t["keyChars"][~mask] == 0)
+        assert np.array_equal(t["keyChars"][mask], chars_o)
+    assert np.array_equal(t["keyRow"], o["firstRowExt"][ext_of_kid])
+    # terms, edges
+    assert np.array_equal(t["termOff"].astype(np.uint64), o["termOff"])
+    assert np.array_equal(t["termChars"], o["termChars"])
+    assert np.array_equal(t["termEdgeOff"], o["termEdgeOff"])
+    assert np.array_equal(t["edgeKid"], o["edgeKid"])
+    assert np.array_equal(t["edgeW"].view(np.uint32), o["edgeW"].view(np.uint32))
+    # gram table + postings
+    assert np.array_equal(ix.gram_units(t), o["gramUnits"])
+    assert np.array_equal(t["gramOff"].astype(np.uint64), o["gramOff"])
+    assert np.array_equal(t["postings"], o["postings"])
+    return t, o
+
+
+def check_search(ix, S, queries, threshold, limit, o=None):
+    o = o or S.tables()
+    r = ix.search_batch(queries, threshold, limit)
+    counts, ext, sc = S.search_batch(queries, threshold, limit)
+    nq = len(queries)
+    assert len(r) == nq
+    got_counts = np.diff(r.offsets)
+    assert np.array_equal(got_counts, counts), np.nonzero(got_counts != counts)[0][:10]
+    kid_of_ext = o["kidOfExt"]
+    for q in range(nq):
+        n = int(counts[q])
+        kids, scores, _, _ = r.query(q)
+        assert np.array_equal(scores.view(np.uint32), sc[q, :n].view(np.uint32)), (q, scores[:8], sc[q, :8])
+        assert np.array_equal(kids, kid_of_ext[ext[q, :n]]), (q, kids[:8], kid_of_ext[ext[q, :8]])
+    return r
+
+
+def test_searchtest_fixture_handle_abi(ssb):
+    """SearchTest/test.cpp:7-18 through the as-shipped exports (rowSize=1)."""
+    from conftest import SEVEN
+    H = ssb.HandleLibrary()
+    h = H.indexN(SEVEN, 1)
+    assert h >= 1
+    assert H.lib.getSize(h) == 7
+    assert H.lib.getLibSize(h) == 16
+    res = H.score(h, "LWMS", 0.5, 2 ** 31 - 1)
+    assert [(k, s) for k, s in res] == [(b"LWMS", 100.0), (b"LWM", 0.75), (b"LWMA", 0.75), (b"LWYY", 0.5)]
+    assert H.search(h, "LWMS", 0.5, 0) == [b"LWMS", b"LWM", b"LWMA", b"LWYY"]
+    assert H.score(h, "   ", 0.0, 0) == []
+    assert len(H.score(h, "*", 0.0, 0)) == 7
+    assert H.score(9999, "LWMS", 0.0, 0) == []           # unknown handle => 0 (dllmain.cpp:69)
+    h2 = H.indexN(SEVEN, 7)
+    assert h2 == h + 1 and H.lib.getSize(h2) == 7 and H.lib.getLibSize(h2) == 16
+    assert {k for k, _ in H.score(h2, "LWMA", 0.0, 0)} == {b"LWMS"}
+    H.lib.dispose(h)
+    assert H.lib.getSize(h) == 0
+    assert H.indexN(SEVEN, 1) == h                        # smallest free handle is reused (dllmain.cpp:41-46)
+    h1 = H.indexN([b"LWMS"], 1)                           # size < 2 => handle, nothing indexed (nGramSearch.hpp:122)
+    assert h1 >= 1 and H.lib.getSize(h1) == 0 and H.score(h1, "LWMS", 0.0, 0) == []
+
+
+def test_golden_fixture(ssb, oracle_built):
+    with open(GOLDEN) as f:
+        cases = json.load(f)["cases"]
+    for case in cases:
+        words = [None if w is None else bytes.fromhex(w) for w in case["words"]]
+        weights = None if case["weights"] is None else np.array(case["weights"], np.float32)
+        S = oracle_built.SpecIndex(words, case["rowSize"], weights)
+        with ssb.Index(words, case["rowSize"], weights) as ix:
+            assert ix.size() == case["getSize"] and ix.lib_size() == case["getLibSize"]
+            _, o = check_tables(ix, S)
+            keys = spec_keys(o) if o["K"] else []
+            for q in case["queries"]:
+                query = bytes.fromhex(q["q"])
+                r = ix.search_batch([query], q["threshold"], q["limit"], strings=True)
+                ours = list(zip(r.strings, r.scores.tolist()))
+                ref = [(bytes.fromhex(k), np.uint32(b).view(np.float32).item()) for k, b in q["results"]]
+                cut = q["limit"] > 0 and len(ref) == q["limit"]
+                assert_same_modulo_ties(ref, ours, cut, what=f"{case['name']} q={query!r}")
+                ext, sc = S.search(query, q["threshold"], q["limit"])
+                assert [k for k, _ in ours] == [keys[e] for e in ext]
+                assert np.array_equal(r.scores.view(np.uint32), sc.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,nq,th,limit", [(10000, 512, 0.0, 100), (10000, 128, 0.3, 100), (200000, 256, 0.0, 100)])
+def test_c1_ascii_rowsize1(ssb, oracle_built, n, nq, th, limit):
+    """C1 / C4 shape: ASCII keys of 6-16 letters, rowSize=1, gSize=3 (fast path: identity + uniform weights)."""
+    from stringsearchlib_b200 import synth
+    keys = synth.ascii_keys(n)
+    S = oracle_built.SpecIndex(keys, 1)
+    with ssb.Index(keys, 1) as ix:
+        info = ix.info()
+        assert info["identity"] and info["uniformW"]
+        _, o = check_tables(ix, S)
+        q = synth.queries_from(keys, nq)
+        check_search(ix, S, q, th, limit, o)
+        # unmodified keys are exact matches: promoted to 100 (nGramSearch.hpp:333-335) only if the key is upper-case;
+        # these keys are lower-case, so the top score is 1.0
+        r = ix.search_batch(keys.slice(0, 8), 0.0, 3, strings=True)
+        for i in range(8):
+            k, s, _, strs = r.query(i)
+            assert strs[0] == keys.get(i) and s[0] == 1.0
+        _, _, st = ix.search_resident(8, 0.0, 3)
+        assert st["nFast"] == 8 and st["nDense"] == 0
+
+
+def test_c2_rowsize2_weights(ssb, oracle_built):
+    """C2 shape (scaled): rows (key, description), per-word weights, threshold 0.3 and 0."""
+    from stringsearchlib_b200 import synth
+    words, w = synth.key_desc_rows(40000)
+    S = oracle_built.SpecIndex(words, 2, w)
+    with ssb.Index(words, 2, w) as ix:
+        _, o = check_tables(ix, S)
+        q = synth.queries_from(words, 300, stride=2)
+        check_search(ix, S, q, 0.3, 100, o)
+        check_search(ix, S, q, 0.0, 10, o)
+        # description words as queries (several terms point to one key)
+        dq = [words.get(2 * i + 1).split(b" ")[0] for i in range(100)]
+        check_search(ix, S, dq, 0.0, 20, o)
+
+
+def test_c3_wide_gsize2(ssb, oracle_built):
+    """C3 shape (scaled): indexW-style UTF-32 rows in U+4E00..U+9FFF, gSize=2, limit 50."""
+    from stringsearchlib_b200 import synth
+    keys = synth.wide_keys(30000)
+    S = oracle_built.SpecIndex(keys, 1, None, 2)
+    with ssb.Index(keys, 1, None, 2) as ix:
+        assert ix.info()["unit"] == 4
+        _, o = check_tables(ix, S)
+        q = synth.queries_from(keys, 200)
+        check_search(ix, S, q, 0.0, 50, o)
+        check_search(ix, S, q, 0.5, 50, o)
+
+
+@pytest.mark.parametrize("g", [2, 3, 4, 5])
+def test_gsize_sweep(ssb, oracle_built, g):
+    """C5 shape (scaled): gSize 2-5, threshold 0.5, limit 1000."""
+    from stringsearchlib_b200 import synth
+    keys = synth.ascii_keys(20000)
+    S = oracle_built.SpecIndex(keys, 1, None, g)
+    with ssb.Index(keys, 1, None, g) as ix:
+        _, o = check_tables(ix, S)
+        q = synth.queries_from(keys, 128)
+        check_search(ix, S, q, 0.5, 1000, o)
+        check_search(ix, S, q, 0.0, 1000, o)
+
+
+@pytest.mark.parametrize("seed,rows,rs", [(1, 3000, 1), (2, 2000, 3), (3, 1500, 2)])
+def test_messy_corpus_all_paths(ssb, oracle_built, seed, rows, rs):
+    """duplicates, blank/NULL cells, invalid characters, zero weights, short terms (edit-distance path,
+    nGramSearch.hpp:182-270), wildcard, limit 0 (unlimited) -> exercises the dense path and many-to-many edges."""
+    rng = np.random.default_rng(seed)
+    words, w = random_corpus(rng, rows, rs, weighted=(seed != 1), max_len=14)
+    S = oracle_built.SpecIndex(words, rs, w)
+    with ssb.Index(words, rs, w) as ix:
+        _, o = check_tables(ix, S)
+        pool = [x for x in words if x]
+        qs = []
+        for _ in range(150):
+            b = bytearray(pool[int(rng.integers(len(pool)))])
+            if b and rng.random() < 0.6:
+                b[int(rng.integers(len(b)))] = int(rng.choice(list(b"abcABC12 .#")))
+            qs.append(bytes(b))
+        qs += [b"", b"*", b"   ", b"a", b"ab", b"abc", b"#", b"abcabcabcabcabcabcabcabcabcabcabcabcabcabc"]
+        for th, lim in ((0.0, 0), (0.3, 10), (0.0, 100), (0.75, 0)):
+            if seed != 1 and lim == 0:
+                qq = [x for x in qs if x not in (b"", b"*")]    # wildcard over multi-edge keys is order-dependent in the reference
+            else:
+                qq = qs
+            check_search(ix, S, qq, th, lim, o)
+
+
+def test_long_terms_only_fast_generic(ssb, oracle_built):
+    """rowSize=3 rows of long words with weights: fast path in generic mode (edges, weights, per-key max-merge)."""
+    from stringsearchlib_b200 import synth
+    keys = synth.ascii_keys(30000)
+    rng = np.random.default_rng(7)
+    w = rng.choice([0.5, 1.0, 1.5, 2.0], size=30000).astype(np.float32)
+    S = oracle_built.SpecIndex(keys, 3, w)
+    with ssb.Index(keys, 3, w) as ix:
+        info = ix.info()
+        assert not info["identity"] and info["nShort"] == 0
+        _, o = check_tables(ix, S)
+        q = synth.queries_from(keys, 300)
+        r = check_search(ix, S, q, 0.0, 50, o)
+        _, _, st = ix.search_resident(300, 0.0, 50)
+        assert st["nFast"] == 300
+        check_search(ix, S, q, 0.4, 50, o)
+
+
+def test_upper_case_exact_match_promotion(ssb, oracle_built):
+    """exact-match promotion to 100 compares the escaped, NOT upper-cased key with the upper-cased query (hpp:330-335)."""
+    words = [b"ALPHABETIC", b"alphabetic", b"ALPHABETIC!", b" ALPHABETIC ", b"ALPHABETICAL", b"BETA GAMMA", b"beta gamma"]
+    S = oracle_built.SpecIndex(words, 1)
+    with ssb.Index(words, 1) as ix:
+        _, o = check_tables(ix, S)
+        r = check_search(ix, S, [b"alphabetic", b"ALPHABETIC", b"beta gamma", b"alphabetic#"], 0.0, 0, o)
+        res = ix.search("alphabetic")
+        assert res[0][1] == 100.0 and res[0][0] == b"ALPHABETIC"
+
+
+def test_set_valid_char(ssb, oracle_built):
+    """setValidChar (dllmain.cpp:142-151): affects later queries and the exact-match test; the index is not rebuilt."""
+    from stringsearchlib_b200 import synth
+    keys = synth.ascii_keys(5000)
+    S = oracle_built.SpecIndex(keys, 1)
+    with ssb.Index(keys, 1) as ix:
+        o = S.tables()
+        q = [keys.get(i) for i in range(50)]
+        valid = b"abcdefghijklm ABCDEFGHIJKLM"
+        ix.set_valid_char(valid)
+        S.set_valid_char(valid)
+        check_search(ix, S, q, 0.0, 20, o)
+
+
+def test_guid_abi(ssb):
+    """README surface (Readme.md:31-226): index/indexW/index2D/index2DW, search/searchW, release[W], dispose[W], sizes."""
+    from conftest import SEVEN
+    G = ssb.GuidLibrary()
+    G.index(b"lib-a", SEVEN, 1, None, 3)
+    assert G.lib.getSize(b"lib-a") == 7 and G.lib.getLibSize(b"lib-a") == 16
+    assert G.search(b"lib-a", "LWMS", 0.5, 100) == [b"LWMS", b"LWM", b"LWMA", b"LWYY"]
+    assert G.search(b"nope", "LWMS", 0.5, 100) == []
+    G.index2D(b"lib-2d", [[b"apple pie", b"dessert"], [b"beef stew", b"dinner"]], [[1.0, 0.5], [1.0, 0.5]], 3)
+    assert G.search(b"lib-2d", "dessert", 0.0, 10) == [b"apple pie"]
+    G.indexW(b"lib-w", ["中文字符串", "中文检索库", "latin text"], 1, None, 2)
+    assert G.lib.getSizeW(b"lib-w") == 3
+    assert G.searchW(b"lib-w", "中文字符", 0.0, 10)[0] == "中文字符串"
+    G.index2D(b"lib-2dw", [["中文字符串", "描述文本"]] * 2, None, 2, wide=True)
+    assert G.searchW(b"lib-2dw", "描述文本", 0.0, 10) == ["中文字符串"]
+    G.index(b"lib-a", [b"replaced key one", b"replaced key two"], 1, None, 3)      # re-index replaces
+    assert G.lib.getSize(b"lib-a") == 2
+    G.lib.dispose(b"lib-a")
+    G.lib.disposeW(b"lib-w")
+    assert G.lib.getSize(b"lib-a") == 0 and G.lib.getSizeW(b"lib-w") == 0
+    G.lib.dispose(b"never-existed")
+
+
+def test_key_range_shards_merge(ssb, oracle_built):
+    """multi-GPU path on one GPU: N key-range shards -> export records -> merge == unsharded oracle."""
+    import torch
+    from stringsearchlib_b200 import synth
+    from stringsearchlib_b200.api import RECORD_DTYPE, merge_records
+    n, nq, limit = 60000, 200, 20
+    keys = synth.ascii_keys(n)
+    # duplicate some keys across shards: the same key string must collapse in the merge
+    q = synth.queries_from(keys, nq)
+    S = oracle_built.SpecIndex(keys, 1)
+    o = S.tables()
+    counts, ext, sc = S.search_batch(q, 0.0, limit)
+    for shards in (2, 3):
+        bounds = np.linspace(0, n, shards + 1).astype(int)
+        gathered = torch.empty((shards, nq, limit, RECORD_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+        idx = []
+        for s in range(shards):
+            ix = ssb.Index(keys.slice(bounds[s], bounds[s + 1]), 1, row_base=int(bounds[s]))
+            ix.search_batch(q, 0.0, limit)
+            ix.export_records(nq, limit, gathered[s].data_ptr())
+            idx.append(ix)
+        merged = torch.empty((nq, limit, RECORD_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+        mcount = torch.empty(nq, dtype=torch.int32, device="cuda")
+        merge_records(gathered.data_ptr(), shards, nq, limit, merged.data_ptr(), mcount.data_ptr())
+        torch.cuda.synchronize()
+        rec = merged.cpu().numpy().view(RECORD_DTYPE).reshape(nq, limit)
+        mc = mcount.cpu().numpy()
+        assert np.array_equal(mc, counts)
+        for i in range(nq):
+            c = int(counts[i])
+            assert np.array_equal(rec["scoreBits"][i, :c], sc[i, :c].view(np.uint32))
+            assert np.array_equal(rec["row"][i, :c], o["firstRowExt"][ext[i, :c]])
+        for ix in idx:
+            ix.close()
+
+
+def test_properties_full_size(ssb):
+    """size-independent properties at 1M keys (the oracle is not run): sorted scores, deterministic repeat,
+    unmodified key ranks first, resident rerun identical, no dense fallback on this distribution."""
+    from stringsearchlib_b200 import synth
+    n, nq = 1000000, 4096
+    keys = synth.ascii_keys(n)
+    with ssb.Index(keys, 1) as ix:
+        info = ix.info()
+        assert info["K"] == info["T"] <= n and info["G"] == 26 ** 3 and info["identity"]
+        q = synth.queries_from(keys, nq)
+        r1 = ix.search_batch(q, 0.0, 100)
+        r2 = ix.search_batch(q, 0.0, 100)
+        assert np.array_equal(r1.offsets, r2.offsets) and np.array_equal(r1.kids, r2.kids)
+        assert np.array_equal(r1.scores.view(np.uint32), r2.scores.view(np.uint32))
+        assert np.all(np.diff(r1.offsets) == 100)
+        sc = r1.scores.reshape(nq, 100)
+        assert np.all(sc[:, :-1] >= sc[:, 1:])
+        kid = r1.kids.reshape(nq, 100)
+        same = sc[:, :-1] == sc[:, 1:]
+        assert np.all(kid[:, :-1][same] < kid[:, 1:][same])          # ties: kid ascending
+        ms, msk, st = ix.search_resident(nq, 0.0, 100)
+        assert st["nFast"] == nq and st["nDense"] == 0 and st["nOverflow"] == 0
+        exact = ix.search_batch(keys.slice(1000, 1064), 0.0, 5, strings=True)
+        for i in range(64):
+            assert exact.query(i)[3][0] == keys.get(1000 + i)
