@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json): queries/s on a 10M-key ASCII gSize=3 index,
+batch 4096, top-100 (+ index-build keys/s), through the engine's C ABI.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--keys 10000000] [--batch 4096] [--limit 100]
+    python bench.py --impl reference ...      # the reference's own CPU implementation (oracle/_ref) on host cores
+
+A step = one batch of `--batch` queries answered against the whole index.
+  value      queries/s with the batch already resident in HBM (device part only, CUDA events on the engine's stream)
+  e2e        queries/s through ssb_search_batch() with HOST char** queries: packing, H2D, kernels, D2H, marshalling
+  roofline   k_fast_search: algorithmic bytes (4 B per posting of every distinct query gram + 8 B per gram lookup +
+             8 B per result) / its CUDA-event duration, against the measured HBM copy bandwidth
+  N > 1      key-range shards (one process per GPU, torchrun): every rank answers the full batch on its shard, one
+             NCCL all-gather of fixed-size records, merge kernel on every rank; total index size fixed => "strong"
+Every step uses a different query batch and the posting table (>= 360 MB at 10M keys; ~750 MB touched per batch) is
+larger than L2, so no explicit L2 flush is needed.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec (10M-key index, batch 4096, top-100) + index-build keys/sec"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_leg(args, nkeys_sample, nq_sample, threads, steps=1, warmup=0):
+    """the reference's own CPU implementation (oracle/_ref/libref.so: indexN + score) on the host cores.
+    Bounded sample: a prefix of the same vocabulary and the first queries of the same batches."""
+    from oracle import loader
+    from stringsearchlib_b200 import synth
+    if not loader.have_ref():
+        raise RuntimeError("oracle/_ref missing")
+    R = loader.RefLib()
+    keys = synth.ascii_keys(nkeys_sample)
+    t0 = time.perf_counter()
+    h = R.indexN(keys, 1, None)
+    t_build = time.perf_counter() - t0
+    L = R.L
+
+    def run_batch(q):
+        ptrs = q.pointers()
+        nq = len(q)
+        addr = ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_char_p))
+        counts = [0] * threads
+
+        def work(t):
+            res, sc = ctypes.POINTER(ctypes.c_char_p)(), ctypes.POINTER(ctypes.c_float)()
+            c = 0
+            for i in range(t, nq, threads):
+                n = L.score(h, addr[i], ctypes.byref(res), ctypes.byref(sc), ctypes.c_float(args.threshold), args.limit)
+                c += n
+                L.release(h, res, sc)
+            counts[t] = c
+
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return time.perf_counter() - t0, sum(counts)
+
+    times = []
+    for s in range(warmup + steps):
+        q = synth.ascii_queries(nq_sample, nkeys_sample, first_query=s * args.batch)
+        dt, _ = run_batch(q)
+        if s >= warmup:
+            times.append(dt)
+    R.dispose(h)
+    qps = nq_sample * len(times) / sum(times)
+    return dict(qps=qps, build_keys_per_s=nkeys_sample / t_build, build_s=t_build, ms_per_step=1e3 * sum(times) / len(times))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--keys", type=int, default=10_000_000)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--limit", type=int, default=100)
+    ap.add_argument("--threshold", type=float, default=0.0)
+    ap.add_argument("--cpu-keys", type=int, default=1_000_000, help="vocabulary prefix indexed by the CPU reference leg")
+    ap.add_argument("--cpu-queries", type=int, default=256, help="queries per step of the CPU reference leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    workload = f"C4: {args.keys}-key synthetic ASCII vocabulary (6-16 letters), rowSize=1, gSize=3, batch {args.batch}, " \
+               f"threshold {args.threshold:g}, top-{args.limit}"
+    config = {"workload": workload, "keys": args.keys, "batch": args.batch, "limit": args.limit, "threshold": args.threshold,
+              "gSize": 3, "rowSize": 1, "sharding": f"key-range x{world}" if world > 1 else "single shard",
+              "l2": "inputs larger than L2: new query batch every step, ~184 KB of postings per query"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = cores
+        r = reference_leg(args, args.cpu_keys, args.cpu_queries, threads, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
+        sample = f"unmodified reference (oracle/_ref/libref.so): indexN over the first {args.cpu_keys} keys of the vocabulary, " \
+                 f"{args.cpu_queries} queries of each batch per step through score()/release(), {threads} caller threads"
+        line = {"impl": "reference", "metric": METRIC, "value": r["qps"], "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["qps"], "unit": "queries/s", "cores": threads, "kind": "reference", "sample": sample},
+                "index_build_keys_per_s": r["build_keys_per_s"],
+                "e2e": {"value": r["qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import stringsearchlib_b200 as ssb
+    from stringsearchlib_b200 import synth
+    from stringsearchlib_b200.api import RECORD_DTYPE, merge_records
+
+    torch.cuda.set_device(local_rank)
+    ssb.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- index build through the char** entry point (host pointers, like an FFI caller)
+    lo = args.keys * rank // world
+    hi = args.keys * (rank + 1) // world
+    keys = synth.ascii_keys(hi - lo, first=lo)
+    ptrs = keys.pointers()
+    barrier()
+    t0 = time.perf_counter()
+    ix = ssb.Index.from_pointers(ptrs, len(keys), 1, None, 3, False, row_base=lo)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    bms = ix.build_ms()
+    info = ix.info()
+    if world > 1:
+        tb = torch.tensor([t_build], device="cuda")
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        t_build = float(tb.item())
+
+    nsteps = args.warmup + args.steps
+    batches = [synth.ascii_queries(args.batch, args.keys, first_query=s * args.batch) for s in range(nsteps)]
+    qptrs = [b.pointers() for b in batches]
+    rec_bytes = RECORD_DTYPE.itemsize
+    if world > 1:
+        mine = torch.empty((args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
+        gathered = torch.empty((world, args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
+        merged = torch.empty((args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
+        mcount = torch.empty(args.batch, dtype=torch.int32, device="cuda")
+
+    def exchange():
+        ix.export_records(args.batch, args.limit, mine.data_ptr())
+        dist.all_gather_into_tensor(gathered, mine)
+        torch.cuda.synchronize()
+        merge_records(gathered.data_ptr(), world, args.batch, args.limit, merged.data_ptr(), mcount.data_ptr())
+
+    dev_ms, fast_ms, e2e_s, step_s, postings, results = [], [], [], [], [], []
+    sampler = ClockSampler(local_rank)
+    launches0 = 0
+    h2d = d2h = 0
+    for s in range(nsteps):
+        if s == args.warmup:
+            barrier()
+            sampler.start()
+            launches0 = ssb.kernel_launches()
+        timed = s >= args.warmup
+        # (1) end to end through the C ABI with host buffers
+        barrier()
+        t0 = time.perf_counter()
+        r = ix.search_batch_pointers(qptrs[s], args.batch, args.threshold, args.limit)
+        if world > 1:
+            exchange()
+            host_rec = merged.cpu()
+            host_cnt = mcount.cpu()
+        t1 = time.perf_counter()
+        # (2) device part only, the same batch resident in HBM
+        barrier()
+        t2 = time.perf_counter()
+        ms, msk, st = ix.search_resident(args.batch, args.threshold, args.limit)
+        if world > 1:
+            exchange()
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        if timed:
+            e2e_s.append(t1 - t0)
+            step_s.append(t3 - t2)
+            dev_ms.append(ms)
+            fast_ms.append(msk)
+            postings.append(st["postings"])
+            results.append(int(r.offsets[-1]))
+            assert st["nFast"] == args.batch and st["nDense"] == 0, st
+            h2d = int(batches[s].offsets[-1]) + 4 * (args.batch + 1)
+            d2h = 4 * args.batch + 8 * args.batch * args.limit if world == 1 else args.batch * args.limit * rec_bytes + 4 * args.batch
+    barrier()
+    clocks = sampler.stop()
+    launches = ssb.kernel_launches() - launches0
+
+    def agg_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor(x, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    step_s, e2e_s, dev_ms, fast_ms = agg_max(step_s), agg_max(e2e_s), agg_max(dev_ms), agg_max(fast_ms)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # N == 1: the device part is timed by CUDA events on the engine's stream; N > 1: the step spans the engine's stream
+    # and NCCL's, so it is bracketed by barrier + synchronize and wall-clocked (max over ranks)
+    step_ms = float(np.mean(dev_ms)) if world == 1 else 1e3 * float(np.mean(step_s))
+    value = args.batch / (step_ms / 1e3)
+    e2e = args.batch / float(np.mean(e2e_s))
+    peak, peak_src = read_peaks()
+    nlists_est = 8.0 * 9                                         # 8 B x ~9 gram lookups per query (negligible next to postings)
+    algo_bytes = float(np.mean(postings)) * 4.0 + args.batch * nlists_est + 8.0 * float(np.mean(results))
+    k_ms = float(np.mean(fast_ms))
+    achieved = algo_bytes / (k_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get("k_fast_search_dram_bytes_per_launch")
+        except (OSError, ValueError):
+            traffic = None
+    line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * float(np.mean(e2e_s))},
+            "gpu_launches": int(launches),   # kernels launched in the timed region (each step runs the path twice: e2e + resident)
+            "roofline": {"bound": "hbm", "kernel": "k_fast_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms},
+            "index_build": {"keys_per_s": args.keys / t_build, "seconds": t_build, "rank0_ms": bms,
+                            "device_only_keys_per_s": (hi - lo) / max((bms["total"] - bms["pack"]) / 1e3, 1e-9),
+                            "terms": info["T"], "grams": info["G"], "postings": info["P"], "device_bytes": info["deviceBytes"]},
+            "host_cores": cores}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = reference_leg(args, args.cpu_keys, min(args.cpu_queries, args.batch), cores, steps=1, warmup=0)
+            line["cpu_baseline"] = {"value": cb["qps"], "unit": "queries/s", "cores": cores, "kind": "reference",
+                                    "sample": f"unmodified reference (oracle/_ref): indexN over the first {args.cpu_keys} keys, "
+                                              f"{min(args.cpu_queries, args.batch)} queries via score()/release(), {cores} threads",
+                                    "index_build_keys_per_s": cb["build_keys_per_s"]}
+        except Exception as e:  # the reference .so is test infrastructure; its absence must not hide the GPU numbers
+            line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": cores, "kind": "reference", "sample": f"unavailable: {e}"}
+    print(json.dumps(line))
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -28,12 +28,17 @@ def _mix(z):
     return z
 
 
-def draws(seed, first, count, ndraw):
-    """[count, ndraw] uint64 draws for items first..first+count."""
+def draws_at(seed, items, ndraw):
+    """[len(items), ndraw] uint64 draws for arbitrary item indices."""
     with np.errstate(over="ignore"):
-        idx = (np.arange(first, first + count, dtype=np.uint64)[:, None] * np.uint64(STRIDE)
+        idx = (np.asarray(items, dtype=np.uint64)[:, None] * np.uint64(STRIDE)
                + np.arange(1, ndraw + 1, dtype=np.uint64)[None, :])
         return _mix(np.uint64(seed) + idx * GAMMA)
+
+
+def draws(seed, first, count, ndraw):
+    """[count, ndraw] uint64 draws for items first..first+count."""
+    return draws_at(seed, np.arange(first, first + count, dtype=np.uint64), ndraw)
 
 
 class Packed:
@@ -179,3 +184,24 @@ def queries_from(keys, nq, seed=QUERY_SEED, stride=1, alphabet=None):
     sym = alphabet[(r[:, 2] % np.uint64(len(alphabet))).astype(np.int64)]
     units[off[:-1].astype(np.int64) + posn] = sym
     return Packed(units, off)
+
+
+def ascii_keys_at(rows, seed=KEY_SEED):
+    """the ASCII keys of arbitrary global row indices (same stream as ascii_keys)."""
+    r = draws_at(seed, rows, 17)
+    lens = (6 + r[:, 0] % np.uint64(11)).astype(np.int64)
+    u, off = _letters(r[:, 1:], lens, 16)
+    return Packed(u, off)
+
+
+def ascii_queries(nq, nkeys, first_query=0, seed=QUERY_SEED):
+    """query batch over a (possibly sharded) vocabulary of nkeys global rows, generated without materialising the keys:
+    query i = key (r0 % nkeys) with one position overwritten by a random lower-case letter."""
+    r = draws(seed, first_query, nq, 3)
+    pick = r[:, 0] % np.uint64(nkeys)
+    keys = ascii_keys_at(pick)
+    lens = np.diff(keys.offsets).astype(np.uint64)
+    posn = (r[:, 1] % lens).astype(np.int64)
+    units = keys.units.copy()
+    units[keys.offsets[:-1].astype(np.int64) + posn] = (ord("a") + (r[:, 2] % np.uint64(26))).astype(np.uint8)
+    return Packed(units, keys.offsets)
