@@ -34,7 +34,7 @@ namespace {
 
 constexpr uint32_t INF = 0xFFFFFFFFu;
 constexpr int FS_THREADS = 256;
-constexpr int FS_WIN = 8192;                 // posting slots staged per pass
+constexpr int FS_WIN = 16384;                // posting slots staged per pass
 constexpr int FS_WIN_ALLOC = FS_WIN + 64;    // + one bound/sentinel slot per list + the shared INF slot
 constexpr int FS_BUF = 4096;                 // candidate buffer entries (>= 2 * FAST_KLIM)
 constexpr int FS_FIRST_PASS = 2048;          // small first pass: establishes tau early
@@ -218,7 +218,10 @@ struct FastShared {
 	uint32_t exactKey[MAX_QGRAMS + 1]; // ~ordered(value) of a weight-1, unpromoted candidate with count c
 	float sOf[MAX_QGRAMS + 1];         // term score for count c
 	unsigned long long tau;
-	uint32_t bufCount, overflow, stride, bound, longest, nActive, query, selPrefixHi, selPrefixLo, selK;
+	uint32_t bufCount, overflow, stride, query, selPrefixLo, selK;
+	uint32_t passLo, passHi, searchTop, cRej;          // term-id range of the pass, top power of two of the binary searches
+	uint32_t qlen, nGrams, cmin, cprom, allOnes;       // per-query scalars (copied from the descriptor)
+	IndexView ix;                                      // the index view, so that non-inlined helpers need no big arguments
 };
 
 __device__ __forceinline__ uint32_t lower_bound_smem(const uint32_t* a, uint32_t n, uint32_t x)
@@ -300,28 +303,84 @@ __device__ void sort_buffer(FastShared& sh, uint32_t n)
 		}
 }
 
-template <class U, int KT>
-__device__ __forceinline__ void merge_pass(const IndexView& ix, FastShared& sh, const QDesc& d, const U* __restrict__ qn, uint32_t nLists)
+// A term reached `c` matches: evaluate its keys (hpp:310-341) and append what can still make the top-k.
+// Called only for terms that survive the integer pre-filter, i.e. rarely once tau is established -> not inlined.
+template <class U>
+__device__ __noinline__ void emit_candidate(FastShared& sh, const U* __restrict__ qn, uint32_t m, uint32_t c)
+{
+	const IndexView& ix = sh.ix;
+	const unsigned long long tau = sh.tau;
+	const uint32_t qlen = sh.qlen, cprom = sh.cprom;
+	if (ix.identity && ix.uniformW) {
+		const uint32_t kid = m;
+		uint32_t hk = sh.exactKey[c];
+		if (c >= cprom && key_equals_query<U>(ix, kid, qn, qlen)) hk = ~float_to_ordered(100.0f);   // hpp:333-335
+		const unsigned long long key = ((unsigned long long)hk << 32) | kid;
+		if (key < tau) {
+			uint32_t idx = atomicAdd(&sh.bufCount, 1u);
+			if (idx < FS_BUF) sh.buf[idx] = key; else sh.overflow = 1;
+		}
+		return;
+	}
+	const float s = sh.sOf[c];
+	const uint32_t cmin = sh.cmin, nGrams = sh.nGrams;
+	for (uint32_t e = ix.termEdgeOff[m]; e < ix.termEdgeOff[m + 1]; ++e) {           // hpp:321-338
+		const uint32_t kid = ix.edgeKid[e];
+		float v = edge_value(ix.edgeW[e], s);
+		const bool prom = c >= cprom && key_equals_query<U>(ix, kid, qn, qlen);
+		if (prom) v = 100.0f;
+		const unsigned long long key = rank_key(v, kid);
+		if (key >= tau) continue;
+		// a key reachable through several terms is emitted once, by the edge with the best value
+		// (per-key max-merge, hpp:326; ties -> smallest term id)
+		bool dominated = false;
+		const uint32_t kb = ix.keyEdgeOff[kid], ke = ix.keyEdgeOff[kid + 1];
+		for (uint32_t x = kb; x < ke && ke - kb > 1 && !dominated; ++x) {
+			const uint32_t t2 = ix.keyEdgeTerm[x];
+			if (t2 == m) continue;
+			const uint32_t c2 = count_for_term<U>(ix, t2, sh.qcode, nGrams);
+			if (c2 < cmin || c2 == 0) continue;
+			float v2 = edge_value(ix.keyEdgeW[x], sh.sOf[c2]);
+			if (c2 >= cprom && (prom || key_equals_query<U>(ix, kid, qn, qlen))) v2 = 100.0f;
+			dominated = v2 > v || (v2 == v && t2 < m);
+		}
+		if (dominated) continue;
+		uint32_t idx = atomicAdd(&sh.bufCount, 1u);
+		if (idx < FS_BUF) sh.buf[idx] = key; else sh.overflow = 1;
+	}
+}
+
+// One pass: every thread owns an equal slice of the pass's term-id range [passLo, passHi), finds its start in each of
+// the K staged windows (branch-free binary searches in lock step) and K-way merges them in registers.
+// The merge yields (term id, match count) in ascending term order without atomics or per-term counters.
+template <class U, int KT, bool ONES>
+__device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__ qn, uint32_t nLists)
 {
 	const int tid = threadIdx.x;
 	const uint32_t stride = sh.stride;
-	const uint32_t j = sh.longest, nj = sh.nTake[j];
-	const uint32_t a0 = (uint32_t)(((unsigned long long)tid * nj) / FS_THREADS);
-	const uint32_t a1 = (uint32_t)(((unsigned long long)(tid + 1) * nj) / FS_THREADS);
-	const uint32_t lo = tid == 0 ? 0u : sh.win[j * stride + a0];
-	const uint32_t hi = (tid == FS_THREADS - 1) ? INF : sh.win[j * stride + a1];
+	const unsigned long long span = (unsigned long long)sh.passHi - sh.passLo;
+	const uint32_t lo = sh.passLo + (uint32_t)((span * (unsigned)tid) / FS_THREADS);
+	const uint32_t hi = (tid == FS_THREADS - 1) ? sh.passHi : sh.passLo + (uint32_t)((span * (unsigned)(tid + 1)) / FS_THREADS);
 	if (lo >= hi) return;
-	uint32_t pos[KT], head[KT];
+	uint32_t pos[KT], head[KT], mu[ONES ? 1 : KT];
+	{
+		uint32_t nT[KT];
 #pragma unroll
-	for (int i = 0; i < KT; ++i) {
-		if ((uint32_t)i < nLists) {
-			const uint32_t* w = sh.win + i * stride;
-			pos[i] = i * stride + (tid == 0 ? 0u : lower_bound_smem(w, sh.nTake[i], lo));
-		} else pos[i] = FS_WIN_ALLOC - 1;          // shared INF slot
-		head[i] = sh.win[pos[i]];
+		for (int i = 0; i < KT; ++i) { nT[i] = sh.nTake[i]; pos[i] = 0; if (!ONES) mu[i] = sh.mult[i]; }
+		for (uint32_t st = sh.searchTop; st > 0; st >>= 1) {
+#pragma unroll
+			for (int i = 0; i < KT; ++i) {
+				const uint32_t q = pos[i] + st;
+				if (q <= nT[i] && sh.win[i * stride + q - 1] < lo) pos[i] = q;
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < KT; ++i) {
+			pos[i] = (uint32_t)i < nLists ? pos[i] + i * stride : FS_WIN_ALLOC - 1;   // template slots beyond K read the INF slot
+			head[i] = sh.win[pos[i]];
+		}
 	}
-	const unsigned long long tau = sh.tau;
-	const uint32_t cmin = d.cmin, cprom = d.cprom, nGrams = d.nGrams;
+	const uint32_t cRej = sh.cRej;
 	while (true) {
 		uint32_t m = head[0];
 #pragma unroll
@@ -330,50 +389,38 @@ __device__ __forceinline__ void merge_pass(const IndexView& ix, FastShared& sh, 
 		uint32_t c = 0;
 #pragma unroll
 		for (int i = 0; i < KT; ++i) {
-			const bool eq = head[i] == m;
-			c += eq ? sh.mult[i] : 0u;
-			pos[i] += eq;
-			if (eq) head[i] = sh.win[pos[i]];
-		}
-		if (c < cmin) continue;                                             // s_t < threshold (hpp:315)
-		// cheap bound: even the best possible value of this term cannot beat the running k-th best
-		if ((((unsigned long long)sh.hiKey[c]) << 32) >= tau) continue;
-		const float s = sh.sOf[c];
-		if (ix.identity && ix.uniformW) {
-			const uint32_t kid = m;
-			uint32_t hk = sh.exactKey[c];
-			if (c >= cprom && key_equals_query<U>(ix, kid, qn, d.qlen)) hk = ~float_to_ordered(100.0f);   // hpp:333-335
-			const unsigned long long key = ((unsigned long long)hk << 32) | kid;
-			if (key < tau) {
-				uint32_t idx = atomicAdd(&sh.bufCount, 1u);
-				if (idx < FS_BUF) sh.buf[idx] = key; else sh.overflow = 1;
-			}
-		} else {
-			for (uint32_t e = ix.termEdgeOff[m]; e < ix.termEdgeOff[m + 1]; ++e) {       // hpp:321-338
-				const uint32_t kid = ix.edgeKid[e];
-				float v = edge_value(ix.edgeW[e], s);
-				const bool prom = c >= cprom && key_equals_query<U>(ix, kid, qn, d.qlen);
-				if (prom) v = 100.0f;
-				const unsigned long long key = rank_key(v, kid);
-				if (key >= tau) continue;
-				// a key reachable through several terms is emitted once, by the edge with the best value
-				// (per-key max-merge, hpp:326; ties -> smallest term id)
-				bool dominated = false;
-				const uint32_t kb = ix.keyEdgeOff[kid], ke = ix.keyEdgeOff[kid + 1];
-				for (uint32_t x = kb; x < ke && ke - kb > 1 && !dominated; ++x) {
-					const uint32_t t2 = ix.keyEdgeTerm[x];
-					if (t2 == m) continue;
-					const uint32_t c2 = count_for_term<U>(ix, t2, sh.qcode, nGrams);
-					if (c2 < cmin || c2 == 0) continue;
-					float v2 = edge_value(ix.keyEdgeW[x], sh.sOf[c2]);
-					if (c2 >= cprom && (prom || key_equals_query<U>(ix, kid, qn, d.qlen))) v2 = 100.0f;
-					dominated = v2 > v || (v2 == v && t2 < m);
-				}
-				if (dominated) continue;
-				uint32_t idx = atomicAdd(&sh.bufCount, 1u);
-				if (idx < FS_BUF) sh.buf[idx] = key; else sh.overflow = 1;
+			if (head[i] == m) {
+				c += ONES ? 1u : mu[i];
+				++pos[i];
+				head[i] = sh.win[pos[i]];
 			}
 		}
+		if (c > cRej) emit_candidate<U>(sh, qn, m, c);
+	}
+}
+
+template <class U, bool ONES>
+__device__ __forceinline__ void merge_dispatch(FastShared& sh, const U* __restrict__ qn, uint32_t nLists)
+{
+	switch (nLists) {
+	case 1: merge_pass<U, 1, ONES>(sh, qn, nLists); break;
+	case 2: merge_pass<U, 2, ONES>(sh, qn, nLists); break;
+	case 3: merge_pass<U, 3, ONES>(sh, qn, nLists); break;
+	case 4: merge_pass<U, 4, ONES>(sh, qn, nLists); break;
+	case 5: merge_pass<U, 5, ONES>(sh, qn, nLists); break;
+	case 6: merge_pass<U, 6, ONES>(sh, qn, nLists); break;
+	case 7: merge_pass<U, 7, ONES>(sh, qn, nLists); break;
+	case 8: merge_pass<U, 8, ONES>(sh, qn, nLists); break;
+	case 9: merge_pass<U, 9, ONES>(sh, qn, nLists); break;
+	case 10: merge_pass<U, 10, ONES>(sh, qn, nLists); break;
+	case 11: merge_pass<U, 11, ONES>(sh, qn, nLists); break;
+	case 12: merge_pass<U, 12, ONES>(sh, qn, nLists); break;
+	case 13: merge_pass<U, 13, ONES>(sh, qn, nLists); break;
+	case 14: merge_pass<U, 14, ONES>(sh, qn, nLists); break;
+	case 15: case 16: merge_pass<U, 16, ONES>(sh, qn, nLists); break;
+	case 17: case 18: case 19: case 20: merge_pass<U, 20, ONES>(sh, qn, nLists); break;
+	case 21: case 22: case 23: case 24: merge_pass<U, 24, ONES>(sh, qn, nLists); break;
+	default: merge_pass<U, 32, ONES>(sh, qn, nLists); break;
 	}
 }
 
@@ -388,7 +435,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_search(IndexView ix, const 
 	FastShared& sh = *reinterpret_cast<FastShared*>(fs_smem);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t nFast = counters[0];
-	if (tid == 0) sh.win[FS_WIN_ALLOC - 1] = INF;
+	if (tid == 0) { sh.win[FS_WIN_ALLOC - 1] = INF; sh.ix = ix; }
 
 	while (true) {
 		__syncthreads();
@@ -418,7 +465,13 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_search(IndexView ix, const 
 			if (c >= d.cprom) ub = fmaxf(ub, 100.0f);
 			sh.hiKey[c] = ~float_to_ordered(ub);
 		}
-		if (tid == 0) { sh.bufCount = 0; sh.overflow = 0; sh.tau = ~0ull; }
+		if (tid == 0) {
+			sh.bufCount = 0; sh.overflow = 0; sh.tau = ~0ull; sh.passLo = 0;
+			sh.qlen = d.qlen; sh.nGrams = nGrams; sh.cmin = d.cmin; sh.cprom = d.cprom;
+			uint32_t ones = 1;
+			for (uint32_t i = 0; i < nLists; ++i) ones &= d.listMult[i] == 1;
+			sh.allOnes = ones;
+		}
 		__syncthreads();
 
 		bool firstPass = true, failed = false, safeMode = false;
@@ -446,32 +499,40 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_search(IndexView ix, const 
 				uint32_t bound = INF;
 				if ((uint32_t)lane < nLists && sh.rem[lane] > wmax) bound = sh.win[lane * stride + wmax];
 				for (int o = 16; o; o >>= 1) bound = min(bound, __shfl_xor_sync(0xffffffffu, bound, o));
-				uint32_t nt = 0;
+				uint32_t nt = 0, last = 0;
 				if ((uint32_t)lane < nLists) {
 					const uint32_t avail = min(sh.rem[lane], wmax);
 					nt = bound == INF ? avail : lower_bound_smem(sh.win + lane * stride, avail, bound);
 					sh.nTake[lane] = nt;
+					if (nt) last = sh.win[lane * stride + nt - 1];
 					sh.win[lane * stride + nt] = INF;
-				}
-				uint32_t best = nt, bi = lane;
+				} else if (lane < MAX_QGRAMS) sh.nTake[lane] = 0;
+				uint32_t best = nt;
 				for (int o = 16; o; o >>= 1) {
-					uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
-					if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+					best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+					last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
 				}
 				if (lane == 0) {
-					sh.stride = stride; sh.longest = bi;
+					sh.stride = stride;
+					sh.passHi = bound == INF ? last + 1 : bound;
+					uint32_t top = 0;
+					if (best) { top = 1; while ((top << 1) <= best) top <<= 1; }
+					sh.searchTop = top;
+					// integer pre-filter: counts c <= cRej can neither pass the threshold nor beat the running k-th best
+					uint32_t rej = sh.cmin ? sh.cmin - 1 : 0;
+					const unsigned long long tau = sh.tau;
+					for (uint32_t c = rej + 1; c <= nGrams; ++c) {
+						if ((((unsigned long long)sh.hiKey[c]) << 32) >= tau) rej = c; else break;
+					}
+					sh.cRej = rej;
 					if (best == 0) sh.overflow = 2;      // no list can advance (corrupt postings): never spin, fall back
 				}
 			}
 			__syncthreads();
 			if (sh.overflow == 2) { failed = true; break; }
 			// ---- merge
-			if (nLists <= 4) merge_pass<U, 4>(ix, sh, d, qn, nLists);
-			else if (nLists <= 8) merge_pass<U, 8>(ix, sh, d, qn, nLists);
-			else if (nLists <= 12) merge_pass<U, 12>(ix, sh, d, qn, nLists);
-			else if (nLists <= 16) merge_pass<U, 16>(ix, sh, d, qn, nLists);
-			else if (nLists <= 24) merge_pass<U, 24>(ix, sh, d, qn, nLists);
-			else merge_pass<U, 32>(ix, sh, d, qn, nLists);
+			if (sh.allOnes) merge_dispatch<U, true>(sh, qn, nLists);
+			else merge_dispatch<U, false>(sh, qn, nLists);
 			__syncthreads();
 			if (sh.overflow) {
 				// the optimistic pass overflowed the candidate buffer: roll it back, make room, redo it with a
@@ -488,7 +549,9 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_search(IndexView ix, const 
 			firstPass = false;
 			if (tid < MAX_QGRAMS && (uint32_t)tid < nLists) { sh.cur[tid] += sh.nTake[tid]; sh.rem[tid] -= sh.nTake[tid]; }
 			level = sh.bufCount;
+			const uint32_t nextLo = sh.passHi;
 			__syncthreads();
+			if (tid == 0) sh.passLo = nextLo;
 			// establish / tighten tau once enough candidates are buffered
 			if (level > k && (sh.tau == ~0ull || level > FS_BUF / 2)) { select_smallest(sh, level, k); level = k; }
 		}
