@@ -234,7 +234,9 @@ def main():
         # (1) end to end through the C ABI with host buffers
         barrier()
         t0 = time.perf_counter()
-        r = ix.search_batch_pointers(qptrs[s], args.batch, args.threshold, args.limit)
+        bp = ix.search_batch_raw(qptrs[s], args.batch, args.threshold, args.limit)   # H2D + kernels + D2H inside
+        n_results = int(bp.contents.offsets[args.batch])
+        ix.free_raw(bp)
         if world > 1:
             exchange()
             host_rec = merged.cpu()
@@ -254,10 +256,10 @@ def main():
             dev_ms.append(ms)
             fast_ms.append(msk)
             postings.append(st["postings"])
-            results.append(int(r.offsets[-1]))
+            results.append(n_results)
             assert st["nFast"] == args.batch and st["nDense"] == 0, st
             h2d = int(batches[s].offsets[-1]) + 4 * (args.batch + 1)
-            d2h = 4 * args.batch + 8 * args.batch * args.limit if world == 1 else args.batch * args.limit * rec_bytes + 4 * args.batch
+            d2h = 4 * (args.batch + 1) + 24 * n_results if world == 1 else args.batch * args.limit * rec_bytes + 4 * args.batch
     barrier()
     clocks = sampler.stop()
     launches = ssb.kernel_launches() - launches0

@@ -257,6 +257,17 @@ class Index:
         """the char** entry point with caller-owned host pointers (what an FFI host passes)."""
         return self._wrap(self._lib.ssb_search_batch(self._h, ptrs, nq, threshold, limit), strings)
 
+    def search_batch_raw(self, ptrs, nq, threshold=0.0, limit=100):
+        """the char** entry point exactly as an FFI host sees it: returns the ssb_batch* (arrays owned by the library,
+        valid until free_raw); no numpy copies — this is what bench.py times as e2e."""
+        bp = self._lib.ssb_search_batch(self._h, ptrs, nq, threshold, limit)
+        if not bp:
+            raise RuntimeError("ssb_search_batch failed: " + self._lib.ssb_last_error().decode())
+        return bp
+
+    def free_raw(self, bp):
+        self._lib.ssb_batch_free(bp)
+
     def search(self, query, threshold=0.0, limit=100):
         """single query: [(key string, score)], like score() of the reference (dllmain.cpp:82)."""
         r = self.search_batch([query], threshold, limit, strings=True)

@@ -61,7 +61,60 @@ inline size_t unit_len(const wchar_t* s) { return wcslen(s); }
 
 }   // namespace
 
+// Pinned result slabs: the arrays an ssb_batch exposes are the D2H destinations themselves (no host-side copies or
+// per-result gathers); ssb_batch_free() returns the slab to its pool.
+struct Slab {
+	void* base = nullptr;
+	size_t bytes = 0;
+	HostResult hr;
+};
+struct SlabPool {
+	std::mutex mu;
+	std::vector<Slab*> free;
+	~SlabPool()
+	{
+		for (Slab* s : free) { cudaFreeHost(s->base); delete s; }
+	}
+	static size_t al(size_t x) { return (x + 63) & ~size_t(63); }
+	Slab* get(size_t capQ, size_t capResults)
+	{
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			for (size_t i = 0; i < free.size(); ++i)
+				if (free[i]->hr.capQ >= capQ && free[i]->hr.capResults >= capResults) {
+					Slab* s = free[i];
+					free.erase(free.begin() + i);
+					return s;
+				}
+		}
+		auto* s = new Slab();
+		capResults = std::max<size_t>(capResults, 1);
+		const size_t oOff = 0, oKid = oOff + al((capQ + 1) * 4), oSc = oKid + al(capResults * 4), oRow = oSc + al(capResults * 4),
+		             oStr = oRow + al(capResults * 8);
+		s->bytes = oStr + al(capResults * 8);
+		SSB_CUDA(cudaMallocHost(&s->base, s->bytes));
+		auto* b = static_cast<uint8_t*>(s->base);
+		s->hr.offsets = reinterpret_cast<uint32_t*>(b + oOff); s->hr.kids = reinterpret_cast<uint32_t*>(b + oKid);
+		s->hr.scores = reinterpret_cast<float*>(b + oSc); s->hr.rows = reinterpret_cast<uint64_t*>(b + oRow);
+		s->hr.strs = reinterpret_cast<uint64_t*>(b + oStr);
+		s->hr.capQ = capQ; s->hr.capResults = capResults;
+		return s;
+	}
+	void put(Slab* s)
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		if (free.size() >= 4) { cudaFreeHost(s->base); delete s; return; }
+		free.push_back(s);
+	}
+};
+struct BatchImpl {
+	ssb_batch pub;                       // must stay the first member: ssb_batch* <-> BatchImpl*
+	std::shared_ptr<SlabPool> pool;
+	Slab* slab = nullptr;
+};
+
 struct ssb_index {
+	std::shared_ptr<SlabPool> pool = std::make_shared<SlabPool>();
 	DeviceIndex dix;
 	HostKeys hk;
 	SearchWorkspace ws;
@@ -156,7 +209,8 @@ ssb_index* create_from_packed(const void* units, const uint64_t* offsets, const 
 
 ssb_batch* marshal(ssb_index* ix, const BatchOutput& out)
 {
-	auto* b = new ssb_batch();
+	auto* impl = new BatchImpl();
+	ssb_batch* b = &impl->pub;
 	b->nq = out.nq;
 	b->offsets = new uint32_t[out.nq + 1];
 	uint64_t total = 0;
@@ -185,6 +239,40 @@ ssb_batch* marshal(ssb_index* ix, const BatchOutput& out)
 		b->strings[i] = chars + (size_t)ix->hk.off[kid] * unit;
 	}
 	return b;
+}
+
+// one batch: pinned slab as the D2H destination; falls back to heap marshalling when a result list exceeds the stride
+ssb_batch* run_batch(ssb_index* ix, const void* units, const uint32_t* offsets, uint32_t nq, float threshold, uint32_t limit)
+{
+	const uint32_t lim = limit == 0 ? 0x7FFFFFFFu : limit;
+	const size_t stride = std::min<uint32_t>(lim, FAST_KLIM);
+	Slab* slab = ix->pool->get(nq, (size_t)nq * stride);
+	slab->hr.strBase = reinterpret_cast<uint64_t>(ix->hk.chars.data());
+	BatchOutput out;
+	try {
+		search_batch(ix->dix, ix->ws, units, offsets, nq, threshold, limit, out, ix->stream, &ix->lastStats, &slab->hr);
+	} catch (...) {
+		ix->pool->put(slab);
+		throw;
+	}
+	if (!out.csr) {
+		ix->pool->put(slab);
+		if (!ix->dix.indexed || nq == 0 || ix->dix.K == 0) {
+			out.nq = nq;
+			out.count.assign(nq, 0);
+		}
+		return marshal(ix, out);
+	}
+	auto* impl = new BatchImpl();
+	impl->pool = ix->pool;
+	impl->slab = slab;
+	impl->pub.nq = nq;
+	impl->pub.offsets = slab->hr.offsets;
+	impl->pub.kids = slab->hr.kids;
+	impl->pub.scores = slab->hr.scores;
+	impl->pub.rows = slab->hr.rows;
+	impl->pub.strings = reinterpret_cast<const void**>(slab->hr.strs);
+	return &impl->pub;
 }
 
 template <class F> auto guarded(F f, decltype(f()) fail) -> decltype(f())
@@ -312,9 +400,7 @@ SSB_API ssb_batch* ssb_search_batch_packed(ssb_index* ix, const void* units, con
 	return guarded([&]() -> ssb_batch* {
 		g_engine.init();
 		std::lock_guard<std::mutex> lk(ix->mu);
-		BatchOutput out;
-		search_batch(ix->dix, ix->ws, units, offsets, nq, threshold, limit, out, ix->stream, &ix->lastStats);
-		return marshal(ix, out);
+		return run_batch(ix, units, offsets, nq, threshold, limit);
 	}, nullptr);
 }
 SSB_API ssb_batch* ssb_search_batch(ssb_index* ix, const void* const* queries, uint32_t nq, float threshold, uint32_t limit)
@@ -336,16 +422,16 @@ SSB_API ssb_batch* ssb_search_batch(ssb_index* ix, const void* const* queries, u
 		ix->pinQ.reserve(std::max<uint64_t>(total * unit, 16));
 		for (uint32_t q = 0; q < nq; ++q)
 			if (queries[q]) memcpy(ix->pinQ.get() + (size_t)off[q] * unit, queries[q], (size_t)(off[q + 1] - off[q]) * unit);
-		BatchOutput out;
-		search_batch(ix->dix, ix->ws, ix->pinQ.get(), off, nq, threshold, limit, out, ix->stream, &ix->lastStats);
-		return marshal(ix, out);
+		return run_batch(ix, ix->pinQ.get(), off, nq, threshold, limit);
 	}, nullptr);
 }
 SSB_API void ssb_batch_free(ssb_batch* b)
 {
 	if (!b) return;
-	delete[] b->offsets; delete[] b->kids; delete[] b->scores; delete[] b->rows; delete[] b->strings;
-	delete b;
+	auto* impl = reinterpret_cast<BatchImpl*>(b);
+	if (impl->slab) impl->pool->put(impl->slab);
+	else { delete[] b->offsets; delete[] b->kids; delete[] b->scores; delete[] b->rows; delete[] b->strings; }
+	delete impl;
 }
 SSB_API int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uint32_t limit, float ms[2], uint64_t stats[4])
 {

@@ -691,6 +691,36 @@ __global__ void k_dense_emit(const uint64_t* __restrict__ sorted, uint32_t n, ui
 	if (i < n) { kid[i] = (uint32_t)sorted[i]; score[i] = rank_key_score(sorted[i]); }
 }
 
+// ---------------------------------------------------------------------------------------------- CSR finalisation
+__global__ void k_clamp_counts(const uint32_t* __restrict__ outCount, uint32_t nq, uint32_t stride, uint32_t* __restrict__ clamped,
+                               uint32_t* __restrict__ anyBig)
+{
+	uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= nq) return;
+	uint32_t c = outCount[q];
+	if (c > stride) { c = 0; *anyBig = 1; }       // 0xFFFFFFFF marks a result list delivered out of band
+	clamped[q] = c;
+}
+// one warp per query: fixed-stride rows -> CSR, plus the key's global row and the host address of its string
+__global__ void __launch_bounds__(256) k_finalize_csr(const uint32_t* __restrict__ count, const uint32_t* __restrict__ off,
+                                                      const uint32_t* __restrict__ outKid, const float* __restrict__ outScore,
+                                                      uint32_t nq, uint32_t stride, const uint32_t* __restrict__ keyOff,
+                                                      const uint64_t* __restrict__ keyRow, uint64_t strBase, uint32_t unit,
+                                                      uint32_t* __restrict__ csrKid, float* __restrict__ csrScore,
+                                                      uint64_t* __restrict__ csrRow, uint64_t* __restrict__ csrStr)
+{
+	const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (q >= nq) return;
+	const uint32_t n = count[q], o = off[q];
+	for (uint32_t i = lane; i < n; i += 32) {
+		const uint32_t kid = outKid[(size_t)q * stride + i];
+		csrKid[o + i] = kid;
+		csrScore[o + i] = outScore[(size_t)q * stride + i];
+		csrRow[o + i] = keyRow[kid];
+		csrStr[o + i] = strBase + (uint64_t)keyOff[kid] * unit;
+	}
+}
+
 inline unsigned grid_for(size_t n, int tpb = 256) { return (unsigned)std::max<size_t>(1, (n + tpb - 1) / tpb); }
 
 template <class U>
@@ -785,6 +815,8 @@ void ensure_workspace(SearchWorkspace& ws, uint32_t nq, size_t charBytes, uint32
 		uint32_t cq = std::max(nq, ws.capQ), st = std::max(stride, ws.stride);
 		ws.qoff.alloc(cq + 1, s); ws.desc.alloc(cq, s); ws.fastList.alloc(cq, s); ws.denseList.alloc(cq, s);
 		ws.outCount.alloc(cq, s); ws.outKid.alloc((size_t)cq * st, s); ws.outScore.alloc((size_t)cq * st, s);
+		ws.csrCount.alloc(cq + 1, s); ws.csrOff.alloc(cq + 1, s); ws.csrKid.alloc((size_t)cq * st, s); ws.csrScore.alloc((size_t)cq * st, s);
+		ws.csrRow.alloc((size_t)cq * st, s); ws.csrStr.alloc((size_t)cq * st, s);
 		ws.capQ = cq; ws.stride = st;
 	}
 	if (charBytes > ws.capChars) {
@@ -857,7 +889,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 }   // namespace
 
 void search_batch(const DeviceIndex& ix, SearchWorkspace& ws, const void* qchars, const uint32_t* qoff, uint32_t nq, float threshold,
-                  uint32_t limit, BatchOutput& out, cudaStream_t s, SearchStats* stats)
+                  uint32_t limit, BatchOutput& out, cudaStream_t s, SearchStats* stats, HostResult* hr)
 {
 	out = BatchOutput();
 	out.nq = nq;
@@ -872,6 +904,29 @@ void search_batch(const DeviceIndex& ix, SearchWorkspace& ws, const void* qchars
 	SSB_CUDA(cudaMemcpyAsync(ws.qoff.get(), qoff, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
 	if (ix.unit == 1) run_device<uint8_t>(ix, ws, nq, threshold, limit, stride, &out, s, stats);
 	else run_device<uint32_t>(ix, ws, nq, threshold, limit, stride, &out, s, stats);
+	if (hr && out.big.empty() && ix.K && hr->capQ >= nq && hr->capResults >= (size_t)nq * stride) {
+		// device-side CSR compaction + gather of row ids / string addresses, D2H straight into the caller's pinned arrays
+		uint32_t* anyBig = ws.counters.get() + 4;
+		k_clamp_counts<<<grid_for(nq), 256, 0, s>>>(ws.outCount.get(), nq, stride, ws.csrCount.get(), anyBig);
+		SSB_LAUNCH_CHECK();
+		exclusive_scan_u32_u32(ws.csrCount.get(), ws.csrOff.get(), nq, ws.csrOff.get() + nq, s);
+		k_finalize_csr<<<grid_for((size_t)nq * 32), 256, 0, s>>>(ws.csrCount.get(), ws.csrOff.get(), ws.outKid.get(), ws.outScore.get(), nq,
+		                                                       stride, ix.keyOff.get(), ix.keyRow.get(), hr->strBase, (uint32_t)ix.unit,
+		                                                       ws.csrKid.get(), ws.csrScore.get(), ws.csrRow.get(), ws.csrStr.get());
+		SSB_LAUNCH_CHECK();
+		SSB_CUDA(cudaMemcpyAsync(hr->offsets, ws.csrOff.get(), (size_t)(nq + 1) * 4, cudaMemcpyDeviceToHost, s));
+		SSB_CUDA(cudaStreamSynchronize(s));
+		const size_t total = hr->offsets[nq];
+		if (total) {
+			SSB_CUDA(cudaMemcpyAsync(hr->kids, ws.csrKid.get(), total * 4, cudaMemcpyDeviceToHost, s));
+			SSB_CUDA(cudaMemcpyAsync(hr->scores, ws.csrScore.get(), total * 4, cudaMemcpyDeviceToHost, s));
+			SSB_CUDA(cudaMemcpyAsync(hr->rows, ws.csrRow.get(), total * 8, cudaMemcpyDeviceToHost, s));
+			SSB_CUDA(cudaMemcpyAsync(hr->strs, ws.csrStr.get(), total * 8, cudaMemcpyDeviceToHost, s));
+			SSB_CUDA(cudaStreamSynchronize(s));
+		}
+		out.csr = true;
+		return;
+	}
 	out.kid.resize((size_t)nq * stride);
 	out.score.resize((size_t)nq * stride);
 	SSB_CUDA(cudaMemcpyAsync(out.count.data(), ws.outCount.get(), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));

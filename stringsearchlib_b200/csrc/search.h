@@ -46,6 +46,10 @@ struct SearchWorkspace {
 	// results (fixed stride)
 	DevBuf<uint32_t> outCount, outKid;
 	DevBuf<float> outScore;
+	// CSR-compacted results incl. the per-result row id and host string pointer (gathered on the device)
+	DevBuf<uint32_t> csrCount, csrOff, csrKid;
+	DevBuf<float> csrScore;
+	DevBuf<uint64_t> csrRow, csrStr;
 	// dense scratch
 	DevBuf<uint32_t> cnt, entry;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -54,8 +58,20 @@ struct SearchWorkspace {
 	~SearchWorkspace();
 };
 
+// Pinned host destination of one batch in CSR form (the arrays an ssb_batch hands to the caller).
+struct HostResult {
+	uint32_t* offsets = nullptr;   // [capQ+1]
+	uint32_t* kids = nullptr;      // [capResults]
+	float* scores = nullptr;
+	uint64_t* rows = nullptr;
+	uint64_t* strs = nullptr;      // host pointers: strBase + keyOff[kid] * unit
+	size_t capQ = 0, capResults = 0;
+	uint64_t strBase = 0;          // address of the host key table
+};
+
 struct BatchOutput {
 	uint32_t nq = 0, stride = 0;
+	bool csr = false;                     // true: results were delivered into the HostResult arrays
 	std::vector<uint32_t> count;          // [nq] results per query
 	std::vector<uint32_t> kid;            // [nq*stride]
 	std::vector<float> score;             // [nq*stride]
@@ -65,8 +81,10 @@ struct BatchOutput {
 
 // queries: packed units (1 or 4 bytes each as ix.unit) + offsets [nq+1] on the HOST.
 // Runs H2D -> kernels -> D2H. Results are kids (rank ids); HostKeys maps them to strings.
+// When hr != nullptr and no query overflowed the fixed stride, the device compacts the results to CSR, gathers row ids and
+// string pointers, and copies straight into hr (out.csr = true); otherwise the fixed-stride arrays of `out` are filled.
 void search_batch(const DeviceIndex& ix, SearchWorkspace& ws, const void* qchars, const uint32_t* qoff, uint32_t nq, float threshold,
-                  uint32_t limit, BatchOutput& out, cudaStream_t s, SearchStats* stats);
+                  uint32_t limit, BatchOutput& out, cudaStream_t s, SearchStats* stats, HostResult* hr = nullptr);
 
 // Device-resident variant used for kernel-only timing: queries must already have been uploaded by a previous
 // search_batch() call with the same arguments; re-runs prep + fast/dense kernels, leaves results on the device.
