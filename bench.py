@@ -193,11 +193,22 @@ def main():
     hi = args.keys * (rank + 1) // world
     keys = synth.ascii_keys(hi - lo, first=lo)
     ptrs = keys.pointers()
+    # first build = cold (CUDA context, memory pool growth, pinned staging allocation); it is reported separately and the
+    # index-build rate is the steady state of the following builds, like any other warmed-up step of this benchmark
     barrier()
     t0 = time.perf_counter()
     ix = ssb.Index.from_pointers(ptrs, len(keys), 1, None, 3, False, row_base=lo)
-    torch.cuda.synchronize()
-    t_build = time.perf_counter() - t0
+    t_build_cold = time.perf_counter() - t0
+    ix.close()
+    t_builds = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        ix = ssb.Index.from_pointers(ptrs, len(keys), 1, None, 3, False, row_base=lo)   # synchronous: returns a searchable index
+        t_builds.append(time.perf_counter() - t0)
+        if _ < 2:
+            ix.close()
+    t_build = float(np.median(t_builds))
     bms = ix.build_ms()
     info = ix.info()
     if world > 1:
@@ -303,7 +314,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_fast_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms},
-            "index_build": {"keys_per_s": args.keys / t_build, "seconds": t_build, "rank0_ms": bms,
+            "index_build": {"keys_per_s": args.keys / t_build, "seconds": t_build, "cold_first_build_seconds": t_build_cold,
+                            "entry": "ssb_index_create(char**): host packing + H2D + device build + key-table D2H", "rank0_ms": bms,
                             "device_only_keys_per_s": (hi - lo) / max((bms["total"] - bms["pack"]) / 1e3, 1e-9),
                             "terms": info["T"], "grams": info["G"], "postings": info["P"], "device_bytes": info["deviceBytes"]},
             "host_cores": cores}

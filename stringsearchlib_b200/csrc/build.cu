@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <thread>
+#include <vector>
 
 namespace ssb {
 namespace {
@@ -443,7 +445,7 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 	ix.g = gSize; ix.unit = sizeof(U); ix.rowBase = rowBase;
 	ix.validLut.alloc(256, s);
 	SSB_CUDA(cudaMemcpyAsync(ix.validLut.get(), validLut, 256, cudaMemcpyHostToDevice, s));
-	hk = HostKeys();
+	hk.reset();
 	// hpp:122 — fewer than two words (or no array): nothing is indexed and every query returns 0
 	if (pw.n < 2 || !pw.chars || rowSize == 0 || gSize == 0 || gSize > MAX_GSIZE) { SSB_CUDA(cudaStreamSynchronize(s)); return; }
 	if (pw.n >= 0xFFFFFFF0ull || pw.totalUnits >= 0xFFFFFFF0ull) throw std::runtime_error("index: more than 2^32 words/units per shard");
@@ -557,7 +559,6 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 		ix.indexed = true;
 		ix.gramCodes.alloc(1, s); ix.gramOff.alloc(1, s); ix.gramOff.zero(s);
 		SSB_CUDA(cudaStreamSynchronize(s));
-		hk.off.assign(1, 0);
 		if (st) st->msTotal = tAll.lap();
 		return;
 	}
@@ -759,13 +760,27 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 	ix.multiEdgeKeys = hp.multiEdge != 0;
 	ix.wmax = ordered_to_float(hp.wmaxOrdered);
 	ix.maxTermLen = hp.maxTermLen; ix.maxKeyLen = hp.maxKeyLen;
-	hk.off.resize(K + 1);
-	hk.chars.resize((size_t)keyUnits * sizeof(U));
-	hk.row.resize(K);
-	SSB_CUDA(cudaMemcpyAsync(hk.off.data(), ix.keyOff.get(), (K + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-	SSB_CUDA(cudaMemcpyAsync(hk.chars.data(), ix.keyChars.get(), hk.chars.size(), cudaMemcpyDeviceToHost, s));
-	SSB_CUDA(cudaMemcpyAsync(hk.row.data(), ix.keyRow.get(), K * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+	hk.K = K;
+	hk.charBytes = (size_t)keyUnits * sizeof(U);
+	hk.chars = static_cast<uint8_t*>(malloc(hk.charBytes ? hk.charBytes : 1));
+	if (!hk.chars) throw std::runtime_error("index: out of host memory for the key table");
+	const bool bounce = pw.pinnedScratch && pw.pinnedScratchBytes >= hk.charBytes && hk.charBytes > (1u << 20);
+	// D2H into pinned scratch at PCIe speed, then a multi-threaded copy into the pageable table (parallel page faults);
+	// a direct D2H into fresh pageable memory runs at ~2 GB/s
+	SSB_CUDA(cudaMemcpyAsync(bounce ? pw.pinnedScratch : hk.chars, ix.keyChars.get(), hk.charBytes, cudaMemcpyDeviceToHost, s));
 	SSB_CUDA(cudaStreamSynchronize(s));
+	if (bounce) {
+		const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+		std::vector<std::thread> th;
+		const size_t chunk = ((hk.charBytes + nt - 1) / nt + 4095) & ~size_t(4095);
+		for (unsigned t = 0; t < nt; ++t) {
+			const size_t b = (size_t)t * chunk;
+			if (b >= hk.charBytes) break;
+			const size_t e = std::min(hk.charBytes, b + chunk);
+			th.emplace_back([&, b, e] { memcpy(hk.chars + b, static_cast<const uint8_t*>(pw.pinnedScratch) + b, e - b); });
+		}
+		for (auto& t : th) t.join();
+	}
 	ix.indexed = true;                                          // hpp:45
 	if (st) { st->msD2H = tPhase.lap(); st->msTotal = tAll.lap(); }
 }

@@ -83,6 +83,15 @@ public:
 		n_ = n + n / 4 + 16;
 		SSB_CUDA(cudaMallocHost((void**)&p_, n_ * sizeof(T)));
 	}
+	// exactly n elements (contents are NOT preserved)
+	void alloc_exact(size_t n)
+	{
+		if (p_) cudaFreeHost(p_);
+		p_ = nullptr;
+		n_ = n;
+		if (n) SSB_CUDA(cudaMallocHost((void**)&p_, n_ * sizeof(T)));
+	}
+	const T* data() const { return p_; }
 	T* get() const { return p_; }
 	size_t size() const { return n_; }
 private:

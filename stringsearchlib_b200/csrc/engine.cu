@@ -42,19 +42,32 @@ unsigned host_threads()
 	return std::max(1u, std::min(n ? n : 1u, 32u));
 }
 
-template <class F> void parallel_for(uint64_t n, F f)
+// f(chunk index, begin, end) over nt contiguous chunks of [0, n); returns the number of chunks
+template <class F> unsigned parallel_for(uint64_t n, unsigned nt, F f)
 {
-	unsigned nt = (unsigned)std::min<uint64_t>(host_threads(), std::max<uint64_t>(1, n / 65536));
-	if (nt <= 1) { f(0, n); return; }
+	if (nt <= 1) { f(0u, (uint64_t)0, n); return 1; }
 	std::vector<std::thread> th;
 	uint64_t chunk = (n + nt - 1) / nt;
+	unsigned used = 0;
 	for (unsigned t = 0; t < nt; ++t) {
 		uint64_t b = t * chunk, e = std::min(n, b + chunk);
 		if (b >= e) break;
-		th.emplace_back([=] { f(b, e); });
+		th.emplace_back([=] { f(t, b, e); });
+		++used;
 	}
 	for (auto& t : th) t.join();
+	return used;
 }
+
+// Process-wide pinned staging for index(): reused across builds so that steady-state builds do not pay
+// cudaMallocHost for a few hundred MB each time. Guarded by a mutex: one packing at a time.
+struct PackStaging {
+	std::mutex mu;
+	PinBuf<uint64_t> off;
+	PinBuf<uint8_t> isNull;
+	PinBuf<uint8_t> chars;
+	PinBuf<float> wts;
+} g_staging;
 
 inline size_t unit_len(const char* s) { return strlen(s); }
 inline size_t unit_len(const wchar_t* s) { return wcslen(s); }
@@ -152,38 +165,51 @@ ssb_index* create_from_pointers(const C* const* words, uint64_t size, uint16_t r
 	SSB_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
 	auto t0 = std::chrono::steady_clock::now();
 	PackedWords pw;
-	PinBuf<uint64_t> off;
-	PinBuf<uint8_t> isNull;
-	PinBuf<C> chars;
-	PinBuf<float> wts;
+	std::lock_guard<std::mutex> stagingLock(g_staging.mu);
+	auto& off = g_staging.off;
+	auto& isNull = g_staging.isNull;
+	auto& charsBytes = g_staging.chars;
+	auto& wts = g_staging.wts;
 	if (words && size >= 2) {
 		off.reserve(size + 1);
 		isNull.reserve(size);
 		uint64_t* o = off.get();
 		uint8_t* nu = isNull.get();
-		// pass 1: lengths (parallel strlen over the caller's pointers)
-		parallel_for(size, [&](uint64_t b, uint64_t e) {
+		// pass 1: lengths (parallel strlen over the caller's pointers) as chunk-local inclusive prefix sums
+		const unsigned nt = (unsigned)std::min<uint64_t>(host_threads(), std::max<uint64_t>(1, size / 65536));
+		std::vector<uint64_t> chunkSum(nt + 1, 0);
+		parallel_for(size, nt, [&](unsigned t, uint64_t b, uint64_t e) {
+			uint64_t run = 0;
 			for (uint64_t i = b; i < e; ++i) {
 				const C* w = words[i];
 				nu[i] = w == nullptr;
-				o[i + 1] = w ? unit_len(w) : 0;
+				run += w ? unit_len(w) : 0;
+				o[i + 1] = run;
 			}
+			chunkSum[t + 1] = run;
 		});
 		o[0] = 0;
-		for (uint64_t i = 0; i < size; ++i) o[i + 1] += o[i];
-		const uint64_t total = o[size];
-		chars.reserve(std::max<uint64_t>(total, 1));
-		C* c = chars.get();
-		// pass 2: gather code units into one pinned CSR buffer
-		parallel_for(size, [&](uint64_t b, uint64_t e) {
-			for (uint64_t i = b; i < e; ++i)
-				if (words[i]) memcpy(c + o[i], words[i], (o[i + 1] - o[i]) * sizeof(C));
+		for (unsigned t = 0; t < nt; ++t) chunkSum[t + 1] += chunkSum[t];
+		const uint64_t total = chunkSum[nt];
+		charsBytes.reserve((std::max<uint64_t>(total, 1) + size) * sizeof(C));   // + terminators: doubles as the key-table bounce buffer
+		C* c = reinterpret_cast<C*>(charsBytes.get());
+		// pass 2: globalise the offsets and gather the code units into one pinned CSR buffer
+		parallel_for(size, nt, [&](unsigned t, uint64_t b, uint64_t e) {
+			const uint64_t base = chunkSum[t];
+			uint64_t prev = base;      // == global o[b]
+			for (uint64_t i = b; i < e; ++i) {
+				const uint64_t end = o[i + 1] + base;
+				if (words[i]) memcpy(c + prev, words[i], (end - prev) * sizeof(C));
+				o[i + 1] = end;
+				prev = end;
+			}
 		});
 		if (weight) {
 			wts.reserve(size);
 			memcpy(wts.get(), weight, size * sizeof(float));
 		}
 		pw.chars = c; pw.off = o; pw.isNull = nu; pw.weight = weight ? wts.get() : nullptr; pw.n = size; pw.totalUnits = total;
+		pw.pinnedScratch = charsBytes.get(); pw.pinnedScratchBytes = charsBytes.size();
 	}
 	ix->msPack = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	build_index(ix->dix, ix->hk, pw, rowSize, gSize, (int)sizeof(C), rowBase, ix->validLut, ix->stream, &ix->bst);
@@ -220,7 +246,14 @@ ssb_batch* marshal(ssb_index* ix, const BatchOutput& out)
 	b->scores = new float[total ? total : 1];
 	b->rows = new uint64_t[total ? total : 1];
 	b->strings = new const void*[total ? total : 1];
-	const uint8_t* chars = ix->hk.chars.data();
+	const uint8_t* chars = ix->hk.chars;
+	if (total && ix->hk.off.empty()) {       // out-of-band path only: fetch the key offsets / rows once
+		ix->hk.off.resize(ix->dix.K + 1);
+		ix->hk.row.resize(ix->dix.K);
+		SSB_CUDA(cudaMemcpyAsync(ix->hk.off.data(), ix->dix.keyOff.get(), (size_t)(ix->dix.K + 1) * 4, cudaMemcpyDeviceToHost, ix->stream));
+		SSB_CUDA(cudaMemcpyAsync(ix->hk.row.data(), ix->dix.keyRow.get(), (size_t)ix->dix.K * 8, cudaMemcpyDeviceToHost, ix->stream));
+		SSB_CUDA(cudaStreamSynchronize(ix->stream));
+	}
 	const int unit = ix->dix.unit;
 	for (uint32_t q = 0; q < out.nq; ++q) {
 		uint32_t n = out.count[q], o = b->offsets[q];
@@ -247,7 +280,7 @@ ssb_batch* run_batch(ssb_index* ix, const void* units, const uint32_t* offsets, 
 	const uint32_t lim = limit == 0 ? 0x7FFFFFFFu : limit;
 	const size_t stride = std::min<uint32_t>(lim, FAST_KLIM);
 	Slab* slab = ix->pool->get(nq, (size_t)nq * stride);
-	slab->hr.strBase = reinterpret_cast<uint64_t>(ix->hk.chars.data());
+	slab->hr.strBase = reinterpret_cast<uint64_t>(ix->hk.chars);
 	BatchOutput out;
 	try {
 		search_batch(ix->dix, ix->ws, units, offsets, nq, threshold, limit, out, ix->stream, &ix->lastStats, &slab->hr);

@@ -77,9 +77,19 @@ struct DeviceIndex {
 
 // Host copy of what result marshalling needs: the key strings (by kid) with terminators.
 struct HostKeys {
+	// raw bytes (unit-sized elements), each key followed by a 0 unit. Plain malloc'ed memory: page-locking a buffer of
+	// this size costs more than the staged D2H copy into pageable memory.
+	uint8_t* chars = nullptr;
+	size_t charBytes = 0;
+	uint32_t K = 0;
+	// only the out-of-band result path needs these on the host; fetched from the device on first use
 	std::vector<uint32_t> off;    // [K+1] in units
-	std::vector<uint8_t> chars;   // raw bytes (unit-sized elements), each key followed by a 0 unit
 	std::vector<uint64_t> row;    // [K] global first row
+	HostKeys() = default;
+	HostKeys(const HostKeys&) = delete;
+	HostKeys& operator=(const HostKeys&) = delete;
+	~HostKeys() { free(chars); }
+	void reset() { free(chars); chars = nullptr; charBytes = 0; K = 0; off.clear(); row.clear(); }
 };
 
 // Packed input of one index()/indexW() call (host, pinned): CSR of code units.
@@ -90,6 +100,9 @@ struct PackedWords {
 	const float* weight = nullptr;  // [n] or nullptr
 	uint64_t n = 0;
 	uint64_t totalUnits = 0;
+	// optional pinned scratch the build may overwrite once the input has been uploaded (bounce buffer of the key-table D2H)
+	void* pinnedScratch = nullptr;
+	size_t pinnedScratchBytes = 0;
 };
 
 struct BuildStats {
