@@ -6,7 +6,7 @@
 //   wordWeight  -> edgeW                         (parallel to edgeKid)
 //   ngrams      -> gramCodes (sorted) / gramOff / postings (CSR gram -> ascending term ids)
 //   longLib/shortLib -> implicit (term length >= 2*gSize) + shortTerms list
-// Id scheme (identical to oracle/spec/ngram_spec.hpp, which is how parity is bit-exact):
+// Id scheme (the CPU restatement used by the parity tests defines the same ids, which is how parity is bit-exact):
 //   kid     = rank of a key by (length asc, first-occurrence asc)   -> ScoreComparer tie-break == kid asc
 //   term id = rank of a term by (min kid over its edges, first word index)
 #pragma once
