@@ -737,7 +737,8 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 			exclusive_scan_u8_u32(newGram.get(), gramPos.get(), nW, dCount.get() + 1, s);
 			ix.P = d2h_scalar(dCount.get(), s);
 			ix.G = d2h_scalar(dCount.get() + 1, s);
-			ix.postings.alloc(ix.P, s); ix.gramCodes.alloc(ix.G, s); ix.gramOff.alloc(ix.G + 1, s);
+			ix.postings.alloc((size_t)ix.P + 4, s);   // +4: TMA window copies round up to 16 bytes
+			ix.gramCodes.alloc(ix.G, s); ix.gramOff.alloc(ix.G + 1, s);
 			if (ix.packed)
 				k_rle_write<true><<<grid_for(nW), TPB, 0, s>>>(sk, sv, newPair.get(), newGram.get(), pairPos.get(), gramPos.get(), nW,
 				                                               ix.postings.get(), ix.gramCodes.get(), ix.gramOff.get());
@@ -748,7 +749,7 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 			k_set_u32<<<1, 1, 0, s>>>(ix.gramOff.get() + ix.G, ix.P);
 			SSB_LAUNCH_CHECK();
 		} else {
-			ix.gramCodes.alloc(1, s); ix.gramOff.alloc(1, s); ix.gramOff.zero(s); ix.postings.alloc(1, s);
+			ix.gramCodes.alloc(1, s); ix.gramOff.alloc(1, s); ix.gramOff.zero(s); ix.postings.alloc(4, s);
 		}
 	}
 	if (st) { SSB_CUDA(cudaStreamSynchronize(s)); st->msGrams = tPhase.lap(); }

@@ -1,0 +1,486 @@
+// fast_path.cuh — k_fast_search: the fused posting-merge / score / top-k kernel (included by search.cu).
+//
+// One persistent CTA per SM slot; queries are handed out by an atomic cursor. For one query:
+//   * the K posting lists of its distinct grams are consumed in PASSES aligned on term-id ranges: every list
+//     contributes a window of at most W = cap/K postings, the pass covers the term ids below
+//     b = min over lists of (first posting NOT in its window), so every occurrence of a term falls in one pass;
+//   * windows are staged in shared memory by TMA 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx) issued by
+//     warp 0 (one copy per list, 16-byte aligned source, completion on one mbarrier); two CTAs per SM overlap one
+//     CTA's copies with the other's merge, which is why the windows are not double buffered (a second buffer would
+//     halve the window and raise the per-pass search overhead for a ~3 % latency gain);
+//   * each thread owns an equal slice of the pass's term-id range, locates it in all K windows with branch-free
+//     binary searches run in lock step, and K-way merges the windows in registers -> (term, match count), ascending,
+//     without atomics or per-term counters (the reference increments a hash map per posting, nGramSearch.hpp:289-298);
+//   * counts are filtered by an integer bound derived from the running k-th best (tau); survivors are scored with the
+//     reference's float operations and appended to a shared-memory buffer that an in-CTA radix select keeps at <= k;
+//   * the final <= limit entries are bitonic-sorted by (score desc, kid asc) and written out.
+#pragma once
+
+namespace {
+
+constexpr uint32_t INF = 0xFFFFFFFFu;
+constexpr int FS_THREADS = 256;
+constexpr int FS_WIN = 16384;                            // posting slots per staged pass
+constexpr int FS_REGION_PAD = 12;                        // per-list slack: 16-byte alignment shift (<=3) + bound slot + rounding
+constexpr int FS_WIN_ALLOC = FS_WIN + MAX_QGRAMS * FS_REGION_PAD + 16;
+constexpr int FS_BUF = 4096;                             // candidate buffer entries (>= 2 * FAST_KLIM)
+constexpr int FS_FIRST_PASS = 2048;                      // small first pass: establishes tau early
+
+struct PassPlan {
+	uint32_t wbase[MAX_QGRAMS];     // element offset of list i's window inside the stage buffer
+	uint32_t avail[MAX_QGRAMS];     // postings of list i that may be consumed in this pass: min(rem, wmax)
+	uint32_t more[MAX_QGRAMS];      // 1 when the list continues past its window (then window[wmax] is its bound)
+	uint32_t wmax;
+};
+
+struct FastShared {
+	alignas(16) uint32_t win[FS_WIN_ALLOC];
+	alignas(16) unsigned long long buf[FS_BUF];
+	alignas(8) unsigned long long bar;                  // mbarrier of the stage buffer (TMA completion)
+	uint32_t hist[256];
+	PassPlan plan;
+	uint32_t cur[MAX_QGRAMS], rem[MAX_QGRAMS], nTake[MAX_QGRAMS], mult[MAX_QGRAMS], listOff[MAX_QGRAMS];
+	uint32_t winByte[MAX_QGRAMS];                        // byte offset of list i's window from &win[0] (current pass)
+	uint64_t qcode[MAX_QGRAMS];
+	uint32_t hiKey[MAX_QGRAMS + 1];    // ~ordered(upper bound of the value of any edge of a term with count c) incl. promotion
+	uint32_t exactKey[MAX_QGRAMS + 1]; // ~ordered(value) of a weight-1, unpromoted candidate with count c
+	float sOf[MAX_QGRAMS + 1];         // term score for count c
+	unsigned long long tau;
+	uint32_t bufCount, overflow, query, selPrefixLo, selK;
+	uint32_t passLo, passHi, searchTop, cRej, lastPass, prefetched;
+	uint32_t qlen, nGrams, cmin, cprom, allOnes, nLists, total;
+	IndexView ix;
+};
+
+// ---- mbarrier / TMA bulk copy (sm_90+ PTX; SASS: SYNCS.*, UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+	             "l"(src), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+	uint32_t ok = 0;
+	for (uint32_t spin = 0; !ok; ++spin) {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok)
+		             : "r"(smem_u32(bar)), "r"(parity)
+		             : "memory");
+		if (spin > (1u << 24)) __trap();      // a lost TMA completion must never hang the GPU
+	}
+}
+
+__device__ __forceinline__ uint32_t lower_bound_smem(const uint32_t* a, uint32_t n, uint32_t x)
+{
+	uint32_t lo = 0, hi = n;
+	while (lo < hi) {
+		uint32_t mid = (lo + hi) >> 1;
+		if (a[mid] < x) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+
+// keeps the k smallest entries of buf[0..n) (all distinct), sets tau to the k-th smallest. CTA-wide.
+__device__ void select_smallest(FastShared& sh, uint32_t n, uint32_t k)
+{
+	const int tid = threadIdx.x;
+	unsigned long long prefix = 0;
+	uint32_t kk = k;
+	for (int shift = 56; shift >= 0; shift -= 8) {
+		sh.hist[tid] = 0;
+		__syncthreads();
+		for (uint32_t i = tid; i < n; i += FS_THREADS) {
+			unsigned long long v = sh.buf[i];
+			if (shift == 56 || (v >> (shift + 8)) == prefix) atomicAdd(&sh.hist[(uint32_t)(v >> shift) & 255u], 1u);
+		}
+		__syncthreads();
+		if (tid < 32) {
+			uint32_t loc[8], sum = 0;
+#pragma unroll
+			for (int j = 0; j < 8; ++j) { loc[j] = sh.hist[tid * 8 + j]; sum += loc[j]; }
+			uint32_t inc = sum;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
+			uint32_t exc = inc - sum;
+			if (kk > exc && kk <= inc) {
+				uint32_t run = exc;
+#pragma unroll
+				for (int j = 0; j < 8; ++j) {
+					if (kk > run && kk <= run + loc[j]) { sh.selPrefixLo = tid * 8 + j; sh.selK = kk - run; }
+					run += loc[j];
+				}
+			}
+		}
+		__syncthreads();
+		prefix = (prefix << 8) | sh.selPrefixLo;
+		kk = sh.selK;
+	}
+	unsigned long long keep[FS_BUF / FS_THREADS];
+	uint32_t nk = 0;
+	for (uint32_t i = tid; i < n; i += FS_THREADS) {
+		unsigned long long v = sh.buf[i];
+		if (v <= prefix) keep[nk++] = v;
+	}
+	if (tid == 0) { sh.bufCount = 0; sh.tau = prefix; }
+	__syncthreads();
+	for (uint32_t j = 0; j < nk; ++j) sh.buf[atomicAdd(&sh.bufCount, 1u)] = keep[j];
+	__syncthreads();
+}
+
+// ascending bitonic sort of buf[0..n), n <= FS_BUF. CTA-wide.
+__device__ void sort_buffer(FastShared& sh, uint32_t n)
+{
+	uint32_t p = 1;
+	while (p < n) p <<= 1;
+	for (uint32_t i = n + threadIdx.x; i < p; i += FS_THREADS) sh.buf[i] = ~0ull;
+	__syncthreads();
+	for (uint32_t size = 2; size <= p; size <<= 1)
+		for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+			for (uint32_t i = threadIdx.x; i < (p >> 1); i += FS_THREADS) {
+				uint32_t lo = 2 * i - (i & (stride - 1));
+				uint32_t hi = lo + stride;
+				bool up = (lo & size) == 0;
+				unsigned long long a = sh.buf[lo], b = sh.buf[hi];
+				if ((a > b) == up) { sh.buf[lo] = b; sh.buf[hi] = a; }
+			}
+			__syncthreads();
+		}
+}
+
+// A term reached `c` matches: evaluate its keys (hpp:310-341) and append what can still make the top-k.
+// Called only for terms that survive the integer pre-filter, i.e. rarely once tau is established -> not inlined.
+template <class U>
+__device__ __noinline__ void emit_candidate(FastShared& sh, const U* __restrict__ qn, uint32_t m, uint32_t c)
+{
+	const IndexView& ix = sh.ix;
+	const unsigned long long tau = sh.tau;
+	const uint32_t qlen = sh.qlen, cprom = sh.cprom;
+	if (ix.identity && ix.uniformW) {
+		const uint32_t kid = m;
+		uint32_t hk = sh.exactKey[c];
+		if (c >= cprom && key_equals_query<U>(ix, kid, qn, qlen)) hk = ~float_to_ordered(100.0f);   // hpp:333-335
+		const unsigned long long key = ((unsigned long long)hk << 32) | kid;
+		if (key < tau) {
+			uint32_t idx = atomicAdd(&sh.bufCount, 1u);
+			if (idx < FS_BUF) sh.buf[idx] = key; else sh.overflow = 1;
+		}
+		return;
+	}
+	const float s = sh.sOf[c];
+	const uint32_t cmin = sh.cmin, nGrams = sh.nGrams;
+	for (uint32_t e = ix.termEdgeOff[m]; e < ix.termEdgeOff[m + 1]; ++e) {           // hpp:321-338
+		const uint32_t kid = ix.edgeKid[e];
+		float v = edge_value(ix.edgeW[e], s);
+		const bool prom = c >= cprom && key_equals_query<U>(ix, kid, qn, qlen);
+		if (prom) v = 100.0f;
+		const unsigned long long key = rank_key(v, kid);
+		if (key >= tau) continue;
+		// a key reachable through several terms is emitted once, by the edge with the best value
+		// (per-key max-merge, hpp:326; ties -> smallest term id)
+		bool dominated = false;
+		const uint32_t kb = ix.keyEdgeOff[kid], ke = ix.keyEdgeOff[kid + 1];
+		for (uint32_t x = kb; x < ke && ke - kb > 1 && !dominated; ++x) {
+			const uint32_t t2 = ix.keyEdgeTerm[x];
+			if (t2 == m) continue;
+			const uint32_t c2 = count_for_term<U>(ix, t2, sh.qcode, nGrams);
+			if (c2 < cmin || c2 == 0) continue;
+			float v2 = edge_value(ix.keyEdgeW[x], sh.sOf[c2]);
+			if (c2 >= cprom && (prom || key_equals_query<U>(ix, kid, qn, qlen))) v2 = 100.0f;
+			dominated = v2 > v || (v2 == v && t2 < m);
+		}
+		if (dominated) continue;
+		uint32_t idx = atomicAdd(&sh.bufCount, 1u);
+		if (idx < FS_BUF) sh.buf[idx] = key; else sh.overflow = 1;
+	}
+}
+
+// One pass over the staged windows: see the file comment.
+template <class U, int KT, bool ONES>
+__device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__ qn, uint32_t nLists)
+{
+	const int tid = threadIdx.x;
+	const unsigned long long span = (unsigned long long)sh.passHi - sh.passLo;
+	const uint32_t lo = sh.passLo + (uint32_t)((span * (unsigned)tid) / FS_THREADS);
+	const uint32_t hi = (tid == FS_THREADS - 1) ? sh.passHi : sh.passLo + (uint32_t)((span * (unsigned)(tid + 1)) / FS_THREADS);
+	if (lo >= hi) return;
+	const char* winBytes = reinterpret_cast<const char*>(&sh.win[0]);
+	uint32_t pos[KT], head[KT], mu[ONES ? 1 : KT];       // pos: BYTE offsets from winBytes (one LDS, no address math)
+	{
+		uint32_t nT[KT], base[KT];
+#pragma unroll
+		for (int i = 0; i < KT; ++i) {
+			const bool on = (uint32_t)i < nLists;
+			nT[i] = on ? sh.nTake[i] : 0;
+			base[i] = on ? sh.winByte[i] : (uint32_t)((FS_WIN_ALLOC - 1) * 4);       // template slots beyond K read the INF slot
+			pos[i] = 0;
+			if (!ONES) mu[i] = sh.mult[i];
+		}
+		for (uint32_t st = sh.searchTop; st > 0; st >>= 1) {
+#pragma unroll
+			for (int i = 0; i < KT; ++i) {
+				const uint32_t q = pos[i] + st;
+				if (q <= nT[i] && *reinterpret_cast<const uint32_t*>(winBytes + base[i] + (q - 1) * 4) < lo) pos[i] = q;
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < KT; ++i) {
+			pos[i] = base[i] + pos[i] * 4;
+			head[i] = *reinterpret_cast<const uint32_t*>(winBytes + pos[i]);
+		}
+	}
+	const uint32_t cRej = sh.cRej;
+	while (true) {
+		uint32_t m = head[0];
+#pragma unroll
+		for (int i = 1; i < KT; ++i) m = min(m, head[i]);
+		if (m >= hi) break;
+		uint32_t c = 0;
+#pragma unroll
+		for (int i = 0; i < KT; ++i) {
+			if (head[i] == m) {
+				c += ONES ? 1u : mu[i];
+				pos[i] += 4;
+				head[i] = *reinterpret_cast<const uint32_t*>(winBytes + pos[i]);
+			}
+		}
+		if (c > cRej) emit_candidate<U>(sh, qn, m, c);
+	}
+}
+
+template <class U, bool ONES>
+__device__ __forceinline__ void merge_dispatch(FastShared& sh, const U* __restrict__ qn, uint32_t nLists)
+{
+	switch (nLists) {
+	case 1: merge_pass<U, 1, ONES>(sh, qn, nLists); break;
+	case 2: merge_pass<U, 2, ONES>(sh, qn, nLists); break;
+	case 3: merge_pass<U, 3, ONES>(sh, qn, nLists); break;
+	case 4: merge_pass<U, 4, ONES>(sh, qn, nLists); break;
+	case 5: merge_pass<U, 5, ONES>(sh, qn, nLists); break;
+	case 6: merge_pass<U, 6, ONES>(sh, qn, nLists); break;
+	case 7: merge_pass<U, 7, ONES>(sh, qn, nLists); break;
+	case 8: merge_pass<U, 8, ONES>(sh, qn, nLists); break;
+	case 9: merge_pass<U, 9, ONES>(sh, qn, nLists); break;
+	case 10: merge_pass<U, 10, ONES>(sh, qn, nLists); break;
+	case 11: merge_pass<U, 11, ONES>(sh, qn, nLists); break;
+	case 12: merge_pass<U, 12, ONES>(sh, qn, nLists); break;
+	case 13: merge_pass<U, 13, ONES>(sh, qn, nLists); break;
+	case 14: merge_pass<U, 14, ONES>(sh, qn, nLists); break;
+	case 15: case 16: merge_pass<U, 16, ONES>(sh, qn, nLists); break;
+	case 17: case 18: case 19: case 20: merge_pass<U, 20, ONES>(sh, qn, nLists); break;
+	case 21: case 22: case 23: case 24: merge_pass<U, 24, ONES>(sh, qn, nLists); break;
+	default: merge_pass<U, 32, ONES>(sh, qn, nLists); break;
+	}
+}
+
+// warp 0: lays out the windows of one pass in the stage buffer from the cursors (cur, rem) and issues the TMA copies.
+// Returns (uniformly over the warp) whether anything was issued.
+__device__ __forceinline__ bool plan_and_issue(FastShared& sh, uint32_t cur, uint32_t rem, uint32_t cap, const uint32_t* postings, int lane)
+{
+	const uint32_t nLists = sh.nLists;
+	const uint32_t wmax = max(1u, cap / nLists);
+	const uint32_t region = (wmax + 10) & ~3u;                     // <= 3 shift + (wmax + 1) data + round-up to 16 bytes
+	PassPlan& pl = sh.plan;
+	uint32_t bytes = 0;
+	const uint32_t* src = nullptr;
+	uint32_t* dst = nullptr;
+	if ((uint32_t)lane < nLists) {
+		const uint32_t e0 = sh.listOff[lane] + cur;                   // absolute posting index of the cursor
+		const uint32_t shift = e0 & 3u;                                // 16-byte alignment of the global source
+		const uint32_t take = min(rem, wmax + 1);
+		pl.wbase[lane] = lane * region + shift;
+		pl.avail[lane] = min(rem, wmax);
+		pl.more[lane] = rem > wmax;
+		if (take) {
+			bytes = ((shift + take + 3) & ~3u) * 4;
+			src = postings + (e0 - shift);
+			dst = &sh.win[lane * region];
+		}
+	}
+	uint32_t total = bytes;
+	for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+	if (lane == 0) pl.wmax = wmax;
+	if (total == 0) return false;
+	if (lane == 0) {
+		// the buffer was read/written through the generic proxy by the previous pass: order that before the async writes
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		mbar_expect_tx(&sh.bar, total);
+	}
+	__syncwarp();
+	if (bytes) tma_load_1d(dst, src, bytes, &sh.bar);
+	return true;
+}
+
+template <class U>
+__global__ void __launch_bounds__(FS_THREADS) k_fast_search(IndexView ix, const QDesc* __restrict__ desc, const U* __restrict__ qnorm,
+                                                            const uint32_t* __restrict__ fastList, uint32_t* __restrict__ counters,
+                                                            uint32_t* __restrict__ denseList, uint32_t limit, uint32_t outStride,
+                                                            uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
+                                                            float* __restrict__ outScore, unsigned long long* __restrict__ statCounters)
+{
+	extern __shared__ __align__(16) unsigned char fs_smem[];
+	FastShared& sh = *reinterpret_cast<FastShared*>(fs_smem);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t nFast = counters[0];
+	const uint32_t k = limit;
+	if (tid == 0) {
+		sh.win[FS_WIN_ALLOC - 1] = INF;
+		sh.ix = ix;
+		mbar_init(&sh.bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	uint32_t parity = 0;                    // phase parity of the stage barrier (uniform across the CTA)
+
+	while (true) {
+		__syncthreads();
+		if (tid == 0) sh.query = atomicAdd(&counters[2], 1u);
+		__syncthreads();
+		const uint32_t wi = sh.query;
+		if (wi >= nFast) break;
+		const uint32_t q = fastList[wi];
+		const QDesc& d = desc[q];
+		const U* qn = qnorm + d.qbeg;
+		const uint32_t nLists = d.nLists, nGrams = d.nGrams;
+		if (tid < MAX_QGRAMS) {
+			sh.qcode[tid] = (uint32_t)tid < nGrams ? d.qcode[tid] : ~0ull;
+			if ((uint32_t)tid < nLists) {
+				sh.listOff[tid] = d.listOff[tid];
+				sh.cur[tid] = 0; sh.rem[tid] = d.listLen[tid]; sh.mult[tid] = d.listMult[tid];
+			} else { sh.rem[tid] = 0; sh.mult[tid] = 0; sh.nTake[tid] = 0; sh.cur[tid] = 0; sh.listOff[tid] = 0; }
+		}
+		if (tid <= MAX_QGRAMS) {
+			const uint32_t c = tid;
+			float s = (c <= nGrams && nGrams) ? term_score(c, nGrams) : 0.0f;
+			sh.sOf[c] = s;
+			// identity/uniform: the exact value (weight 1); otherwise an upper bound over all edges of any term
+			float ub = ix.uniformW ? edge_value(1.0f, s) : edge_value(ix.wmax, s);
+			sh.exactKey[c] = ~float_to_ordered(edge_value(1.0f, s));
+			if (c >= d.cprom) ub = fmaxf(ub, 100.0f);
+			sh.hiKey[c] = ~float_to_ordered(ub);
+		}
+		if (tid == 0) {
+			sh.bufCount = 0; sh.overflow = 0; sh.tau = ~0ull; sh.passLo = 0; sh.prefetched = 0;
+			sh.qlen = d.qlen; sh.nGrams = nGrams; sh.cmin = d.cmin; sh.cprom = d.cprom; sh.nLists = nLists; sh.total = d.total;
+			uint32_t ones = 1;
+			for (uint32_t i = 0; i < nLists; ++i) ones &= d.listMult[i] == 1;
+			sh.allOnes = ones;
+		}
+		__syncthreads();
+
+		bool failed = false, safeMode = false, more = nLists != 0;
+		uint32_t level = 0;
+		uint32_t cap = d.total > FS_FIRST_PASS ? FS_FIRST_PASS : FS_WIN;      // small first pass: it only has to establish tau
+		while (more) {
+			// ---- warp 0: lay out the windows from the cursors and issue the TMA copies
+			if (warp == 0) {
+				const bool any = plan_and_issue(sh, sh.cur[lane & (MAX_QGRAMS - 1)], (uint32_t)lane < nLists ? sh.rem[lane] : 0, cap,
+				                                ix.postings, lane);
+				if (lane == 0) sh.prefetched = any;
+			}
+			__syncthreads();
+			if (!sh.prefetched) break;
+			mbar_wait(&sh.bar, parity);
+			parity ^= 1;
+			// ---- warp 0: pass bound b = min over lists of the first posting NOT covered; consumed counts; sentinels; pre-filter
+			if (warp == 0) {
+				const PassPlan& pl = sh.plan;
+				const uint32_t wmax = pl.wmax;
+				uint32_t* wb = sh.win;
+				uint32_t bound = INF, wbase = 0, avail = 0;
+				if ((uint32_t)lane < nLists) {
+					wbase = pl.wbase[lane]; avail = pl.avail[lane];
+					if (pl.more[lane]) bound = wb[wbase + wmax];
+				}
+				for (int o = 16; o; o >>= 1) bound = min(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+				uint32_t nt = 0, last = 0;
+				if ((uint32_t)lane < nLists) {
+					nt = bound == INF ? avail : lower_bound_smem(wb + wbase, avail, bound);
+					sh.nTake[lane] = nt;
+					sh.winByte[lane] = wbase * 4;
+					if (nt) last = wb[wbase + nt - 1];
+					wb[wbase + nt] = INF;
+				}
+				uint32_t best = nt;
+				for (int o = 16; o; o >>= 1) {
+					best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+					last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+				}
+				if (lane == 0) {
+					sh.passHi = bound == INF ? last + 1 : bound;
+					uint32_t top = 0;
+					if (best) { top = 1; while ((top << 1) <= best) top <<= 1; }
+					sh.searchTop = top;
+					// integer pre-filter: a count c <= cRej can neither pass the threshold nor beat the running k-th best.
+					// In identity mode kid == term id >= passLo, which makes the bound exact for the tie class of tau.
+					uint32_t rej = sh.cmin ? sh.cmin - 1 : 0;
+					const unsigned long long tau = sh.tau;
+					const unsigned long long lowKid = (sh.ix.identity && sh.ix.uniformW) ? sh.passLo : 0u;
+					for (uint32_t c = rej + 1; c <= nGrams; ++c) {
+						if (((((unsigned long long)sh.hiKey[c]) << 32) | lowKid) >= tau) rej = c; else break;
+					}
+					sh.cRej = rej;
+					sh.lastPass = bound == INF;
+					if (best == 0) sh.overflow = 2;          // no list can advance (corrupt postings): never spin, fall back
+				}
+			}
+			__syncthreads();
+			if (sh.overflow == 2) { failed = true; break; }
+			// ---- merge
+			if (sh.allOnes) merge_dispatch<U, true>(sh, qn, nLists);
+			else merge_dispatch<U, false>(sh, qn, nLists);
+			__syncthreads();
+			if (sh.overflow) {
+				// the optimistic pass overflowed the candidate buffer: roll it back, make room and redo it with a window small
+				// enough to be safe for single-edge terms; if that overflows too -> dense path
+				if (safeMode && level <= k) { failed = true; break; }
+				__syncthreads();
+				if (tid == 0) { sh.bufCount = level; sh.overflow = 0; }
+				__syncthreads();
+				if (level > k) { select_smallest(sh, level, k); level = k; }
+				safeMode = true;
+				cap = min((uint32_t)FS_WIN, (uint32_t)FS_BUF - level);
+				continue;
+			}
+			safeMode = false;
+			cap = FS_WIN;
+			more = sh.lastPass == 0;
+			if (tid < MAX_QGRAMS && (uint32_t)tid < nLists) { sh.cur[tid] += sh.nTake[tid]; sh.rem[tid] -= sh.nTake[tid]; }
+			level = sh.bufCount;
+			const uint32_t nextLo = sh.passHi;
+			__syncthreads();
+			if (tid == 0) sh.passLo = nextLo;
+			// establish tau as soon as k candidates exist, tighten it whenever the buffer grew by half of k again
+			if (level > k && (sh.tau == ~0ull || level >= k + (k >> 1) + 32 || level > FS_BUF / 2)) { select_smallest(sh, level, k); level = k; }
+		}
+		if (failed) {
+			if (tid == 0) {
+				denseList[atomicAdd(&counters[1], 1u)] = q;
+				atomicAdd(&counters[3], 1u);
+			}
+			continue;
+		}
+		// ---- final: top-k, sorted
+		if (level > k) { select_smallest(sh, level, k); level = k; }
+		sort_buffer(sh, level);
+		for (uint32_t i = tid; i < level; i += FS_THREADS) {
+			unsigned long long v = sh.buf[i];
+			outKid[(size_t)q * outStride + i] = (uint32_t)v;
+			outScore[(size_t)q * outStride + i] = rank_key_score(v);
+		}
+		if (tid == 0) {
+			outCount[q] = level;
+			atomicAdd(&statCounters[0], (unsigned long long)d.total);
+		}
+	}
+}
+
+}   // namespace

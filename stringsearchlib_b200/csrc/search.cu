@@ -32,13 +32,6 @@ SearchWorkspace::~SearchWorkspace()
 
 namespace {
 
-constexpr uint32_t INF = 0xFFFFFFFFu;
-constexpr int FS_THREADS = 256;
-constexpr int FS_WIN = 16384;                // posting slots staged per pass
-constexpr int FS_WIN_ALLOC = FS_WIN + 64;    // + one bound/sentinel slot per list + the shared INF slot
-constexpr int FS_BUF = 4096;                 // candidate buffer entries (>= 2 * FAST_KLIM)
-constexpr int FS_FIRST_PASS = 2048;          // small first pass: establishes tau early
-
 struct IndexView {
 	int g, unit, symBits;
 	uint32_t K, T, G, A, nShort;
@@ -206,376 +199,11 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 	}
 }
 
-// ---------------------------------------------------------------------------------------------- fast path
-struct FastShared {
-	uint32_t win[FS_WIN_ALLOC];
-	unsigned long long buf[FS_BUF];
-	uint32_t hist[256];
-	uint32_t cur[MAX_QGRAMS], rem[MAX_QGRAMS], nTake[MAX_QGRAMS], mult[MAX_QGRAMS];
-	const uint32_t* base[MAX_QGRAMS];
-	uint64_t qcode[MAX_QGRAMS];
-	uint32_t hiKey[MAX_QGRAMS + 1];    // ~ordered(upper bound of the value of any edge of a term with count c) incl. promotion
-	uint32_t exactKey[MAX_QGRAMS + 1]; // ~ordered(value) of a weight-1, unpromoted candidate with count c
-	float sOf[MAX_QGRAMS + 1];         // term score for count c
-	unsigned long long tau;
-	uint32_t bufCount, overflow, stride, query, selPrefixLo, selK;
-	uint32_t passLo, passHi, searchTop, cRej;          // term-id range of the pass, top power of two of the binary searches
-	uint32_t qlen, nGrams, cmin, cprom, allOnes;       // per-query scalars (copied from the descriptor)
-	IndexView ix;                                      // the index view, so that non-inlined helpers need no big arguments
-};
+}   // namespace
 
-__device__ __forceinline__ uint32_t lower_bound_smem(const uint32_t* a, uint32_t n, uint32_t x)
-{
-	uint32_t lo = 0, hi = n;
-	while (lo < hi) {
-		uint32_t mid = (lo + hi) >> 1;
-		if (a[mid] < x) lo = mid + 1; else hi = mid;
-	}
-	return lo;
-}
+#include "fast_path.cuh"   // k_fast_search (inside namespace ssb)
 
-// keeps the k smallest entries of buf[0..n) (all distinct), returns the k-th smallest as the new tau. CTA-wide.
-__device__ void select_smallest(FastShared& sh, uint32_t n, uint32_t k)
-{
-	const int tid = threadIdx.x;
-	unsigned long long prefix = 0;
-	uint32_t kk = k;
-	for (int shift = 56; shift >= 0; shift -= 8) {
-		sh.hist[tid] = 0;
-		__syncthreads();
-		for (uint32_t i = tid; i < n; i += FS_THREADS) {
-			unsigned long long v = sh.buf[i];
-			if (shift == 56 || (v >> (shift + 8)) == prefix) atomicAdd(&sh.hist[(uint32_t)(v >> shift) & 255u], 1u);
-		}
-		__syncthreads();
-		if (tid < 32) {
-			// warp scan over 256 bins: lane owns 8 consecutive bins
-			uint32_t loc[8], sum = 0;
-#pragma unroll
-			for (int j = 0; j < 8; ++j) { loc[j] = sh.hist[tid * 8 + j]; sum += loc[j]; }
-			uint32_t inc = sum;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
-			uint32_t exc = inc - sum;
-			if (kk > exc && kk <= inc) {
-				uint32_t run = exc;
-#pragma unroll
-				for (int j = 0; j < 8; ++j) {
-					if (kk > run && kk <= run + loc[j]) { sh.selPrefixLo = tid * 8 + j; sh.selK = kk - run; }
-					run += loc[j];
-				}
-			}
-		}
-		__syncthreads();
-		prefix = (prefix << 8) | sh.selPrefixLo;
-		kk = sh.selK;
-	}
-	// prefix is now the k-th smallest value; compact entries <= prefix to the front
-	unsigned long long keep[FS_BUF / FS_THREADS];
-	uint32_t nk = 0;
-	for (uint32_t i = tid; i < n; i += FS_THREADS) {
-		unsigned long long v = sh.buf[i];
-		if (v <= prefix) keep[nk++] = v;
-	}
-	if (tid == 0) { sh.bufCount = 0; sh.tau = prefix; }
-	__syncthreads();
-	for (uint32_t j = 0; j < nk; ++j) sh.buf[atomicAdd(&sh.bufCount, 1u)] = keep[j];
-	__syncthreads();
-}
-
-// ascending bitonic sort of buf[0..n), n <= FS_BUF. CTA-wide.
-__device__ void sort_buffer(FastShared& sh, uint32_t n)
-{
-	uint32_t p = 1;
-	while (p < n) p <<= 1;
-	for (uint32_t i = n + threadIdx.x; i < p; i += FS_THREADS) sh.buf[i] = ~0ull;
-	__syncthreads();
-	for (uint32_t size = 2; size <= p; size <<= 1)
-		for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-			for (uint32_t i = threadIdx.x; i < (p >> 1); i += FS_THREADS) {
-				uint32_t lo = 2 * i - (i & (stride - 1));
-				uint32_t hi = lo + stride;
-				bool up = (lo & size) == 0;
-				unsigned long long a = sh.buf[lo], b = sh.buf[hi];
-				if ((a > b) == up) { sh.buf[lo] = b; sh.buf[hi] = a; }
-			}
-			__syncthreads();
-		}
-}
-
-// A term reached `c` matches: evaluate its keys (hpp:310-341) and append what can still make the top-k.
-// Called only for terms that survive the integer pre-filter, i.e. rarely once tau is established -> not inlined.
-template <class U>
-__device__ __noinline__ void emit_candidate(FastShared& sh, const U* __restrict__ qn, uint32_t m, uint32_t c)
-{
-	const IndexView& ix = sh.ix;
-	const unsigned long long tau = sh.tau;
-	const uint32_t qlen = sh.qlen, cprom = sh.cprom;
-	if (ix.identity && ix.uniformW) {
-		const uint32_t kid = m;
-		uint32_t hk = sh.exactKey[c];
-		if (c >= cprom && key_equals_query<U>(ix, kid, qn, qlen)) hk = ~float_to_ordered(100.0f);   // hpp:333-335
-		const unsigned long long key = ((unsigned long long)hk << 32) | kid;
-		if (key < tau) {
-			uint32_t idx = atomicAdd(&sh.bufCount, 1u);
-			if (idx < FS_BUF) sh.buf[idx] = key; else sh.overflow = 1;
-		}
-		return;
-	}
-	const float s = sh.sOf[c];
-	const uint32_t cmin = sh.cmin, nGrams = sh.nGrams;
-	for (uint32_t e = ix.termEdgeOff[m]; e < ix.termEdgeOff[m + 1]; ++e) {           // hpp:321-338
-		const uint32_t kid = ix.edgeKid[e];
-		float v = edge_value(ix.edgeW[e], s);
-		const bool prom = c >= cprom && key_equals_query<U>(ix, kid, qn, qlen);
-		if (prom) v = 100.0f;
-		const unsigned long long key = rank_key(v, kid);
-		if (key >= tau) continue;
-		// a key reachable through several terms is emitted once, by the edge with the best value
-		// (per-key max-merge, hpp:326; ties -> smallest term id)
-		bool dominated = false;
-		const uint32_t kb = ix.keyEdgeOff[kid], ke = ix.keyEdgeOff[kid + 1];
-		for (uint32_t x = kb; x < ke && ke - kb > 1 && !dominated; ++x) {
-			const uint32_t t2 = ix.keyEdgeTerm[x];
-			if (t2 == m) continue;
-			const uint32_t c2 = count_for_term<U>(ix, t2, sh.qcode, nGrams);
-			if (c2 < cmin || c2 == 0) continue;
-			float v2 = edge_value(ix.keyEdgeW[x], sh.sOf[c2]);
-			if (c2 >= cprom && (prom || key_equals_query<U>(ix, kid, qn, qlen))) v2 = 100.0f;
-			dominated = v2 > v || (v2 == v && t2 < m);
-		}
-		if (dominated) continue;
-		uint32_t idx = atomicAdd(&sh.bufCount, 1u);
-		if (idx < FS_BUF) sh.buf[idx] = key; else sh.overflow = 1;
-	}
-}
-
-// One pass: every thread owns an equal slice of the pass's term-id range [passLo, passHi), finds its start in each of
-// the K staged windows (branch-free binary searches in lock step) and K-way merges them in registers.
-// The merge yields (term id, match count) in ascending term order without atomics or per-term counters.
-template <class U, int KT, bool ONES>
-__device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__ qn, uint32_t nLists)
-{
-	const int tid = threadIdx.x;
-	const uint32_t stride = sh.stride;
-	const unsigned long long span = (unsigned long long)sh.passHi - sh.passLo;
-	const uint32_t lo = sh.passLo + (uint32_t)((span * (unsigned)tid) / FS_THREADS);
-	const uint32_t hi = (tid == FS_THREADS - 1) ? sh.passHi : sh.passLo + (uint32_t)((span * (unsigned)(tid + 1)) / FS_THREADS);
-	if (lo >= hi) return;
-	uint32_t pos[KT], head[KT], mu[ONES ? 1 : KT];
-	{
-		uint32_t nT[KT];
-#pragma unroll
-		for (int i = 0; i < KT; ++i) { nT[i] = sh.nTake[i]; pos[i] = 0; if (!ONES) mu[i] = sh.mult[i]; }
-		for (uint32_t st = sh.searchTop; st > 0; st >>= 1) {
-#pragma unroll
-			for (int i = 0; i < KT; ++i) {
-				const uint32_t q = pos[i] + st;
-				if (q <= nT[i] && sh.win[i * stride + q - 1] < lo) pos[i] = q;
-			}
-		}
-#pragma unroll
-		for (int i = 0; i < KT; ++i) {
-			pos[i] = (uint32_t)i < nLists ? pos[i] + i * stride : FS_WIN_ALLOC - 1;   // template slots beyond K read the INF slot
-			head[i] = sh.win[pos[i]];
-		}
-	}
-	const uint32_t cRej = sh.cRej;
-	while (true) {
-		uint32_t m = head[0];
-#pragma unroll
-		for (int i = 1; i < KT; ++i) m = min(m, head[i]);
-		if (m >= hi) break;
-		uint32_t c = 0;
-#pragma unroll
-		for (int i = 0; i < KT; ++i) {
-			if (head[i] == m) {
-				c += ONES ? 1u : mu[i];
-				++pos[i];
-				head[i] = sh.win[pos[i]];
-			}
-		}
-		if (c > cRej) emit_candidate<U>(sh, qn, m, c);
-	}
-}
-
-template <class U, bool ONES>
-__device__ __forceinline__ void merge_dispatch(FastShared& sh, const U* __restrict__ qn, uint32_t nLists)
-{
-	switch (nLists) {
-	case 1: merge_pass<U, 1, ONES>(sh, qn, nLists); break;
-	case 2: merge_pass<U, 2, ONES>(sh, qn, nLists); break;
-	case 3: merge_pass<U, 3, ONES>(sh, qn, nLists); break;
-	case 4: merge_pass<U, 4, ONES>(sh, qn, nLists); break;
-	case 5: merge_pass<U, 5, ONES>(sh, qn, nLists); break;
-	case 6: merge_pass<U, 6, ONES>(sh, qn, nLists); break;
-	case 7: merge_pass<U, 7, ONES>(sh, qn, nLists); break;
-	case 8: merge_pass<U, 8, ONES>(sh, qn, nLists); break;
-	case 9: merge_pass<U, 9, ONES>(sh, qn, nLists); break;
-	case 10: merge_pass<U, 10, ONES>(sh, qn, nLists); break;
-	case 11: merge_pass<U, 11, ONES>(sh, qn, nLists); break;
-	case 12: merge_pass<U, 12, ONES>(sh, qn, nLists); break;
-	case 13: merge_pass<U, 13, ONES>(sh, qn, nLists); break;
-	case 14: merge_pass<U, 14, ONES>(sh, qn, nLists); break;
-	case 15: case 16: merge_pass<U, 16, ONES>(sh, qn, nLists); break;
-	case 17: case 18: case 19: case 20: merge_pass<U, 20, ONES>(sh, qn, nLists); break;
-	case 21: case 22: case 23: case 24: merge_pass<U, 24, ONES>(sh, qn, nLists); break;
-	default: merge_pass<U, 32, ONES>(sh, qn, nLists); break;
-	}
-}
-
-template <class U>
-__global__ void __launch_bounds__(FS_THREADS) k_fast_search(IndexView ix, const QDesc* __restrict__ desc, const U* __restrict__ qnorm,
-                                                            const uint32_t* __restrict__ fastList, uint32_t* __restrict__ counters,
-                                                            uint32_t* __restrict__ denseList, uint32_t limit, uint32_t outStride,
-                                                            uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
-                                                            float* __restrict__ outScore, unsigned long long* __restrict__ statCounters)
-{
-	extern __shared__ __align__(16) unsigned char fs_smem[];
-	FastShared& sh = *reinterpret_cast<FastShared*>(fs_smem);
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t nFast = counters[0];
-	if (tid == 0) { sh.win[FS_WIN_ALLOC - 1] = INF; sh.ix = ix; }
-
-	while (true) {
-		__syncthreads();
-		if (tid == 0) sh.query = atomicAdd(&counters[2], 1u);
-		__syncthreads();
-		const uint32_t wi = sh.query;
-		if (wi >= nFast) break;
-		const uint32_t q = fastList[wi];
-		const QDesc& d = desc[q];
-		const U* qn = qnorm + d.qbeg;
-		const uint32_t nLists = d.nLists, nGrams = d.nGrams;
-		const uint32_t k = limit;
-		if (tid < MAX_QGRAMS) {
-			sh.qcode[tid] = (uint32_t)tid < nGrams ? d.qcode[tid] : ~0ull;
-			if ((uint32_t)tid < nLists) {
-				sh.base[tid] = ix.postings + d.listOff[tid];
-				sh.cur[tid] = 0; sh.rem[tid] = d.listLen[tid]; sh.mult[tid] = d.listMult[tid];
-			} else { sh.rem[tid] = 0; sh.mult[tid] = 0; sh.nTake[tid] = 0; }
-		}
-		if (tid <= MAX_QGRAMS) {
-			const uint32_t c = tid;
-			float s = (c <= nGrams && nGrams) ? term_score(c, nGrams) : 0.0f;
-			sh.sOf[c] = s;
-			// identity/uniform: the exact value (weight 1); otherwise an upper bound over all edges of any term
-			float ub = ix.uniformW ? edge_value(1.0f, s) : edge_value(ix.wmax, s);
-			sh.exactKey[c] = ~float_to_ordered(edge_value(1.0f, s));
-			if (c >= d.cprom) ub = fmaxf(ub, 100.0f);
-			sh.hiKey[c] = ~float_to_ordered(ub);
-		}
-		if (tid == 0) {
-			sh.bufCount = 0; sh.overflow = 0; sh.tau = ~0ull; sh.passLo = 0;
-			sh.qlen = d.qlen; sh.nGrams = nGrams; sh.cmin = d.cmin; sh.cprom = d.cprom;
-			uint32_t ones = 1;
-			for (uint32_t i = 0; i < nLists; ++i) ones &= d.listMult[i] == 1;
-			sh.allOnes = ones;
-		}
-		__syncthreads();
-
-		bool firstPass = true, failed = false, safeMode = false;
-		uint32_t level = 0;
-		while (true) {
-			// ---- plan the pass
-			uint32_t nAct = 0;
-			for (uint32_t i = 0; i < nLists; ++i) nAct += sh.rem[i] > 0;
-			if (nAct == 0) break;
-			uint32_t cap = FS_WIN;
-			if (firstPass && d.total > FS_FIRST_PASS) cap = FS_FIRST_PASS;
-			if (safeMode) cap = min(cap, (uint32_t)FS_BUF - level);
-			const uint32_t wmax = max(1u, cap / nLists);        // regions are laid out for all lists (exhausted ones stay empty)
-			const uint32_t stride = wmax + 1;
-			// ---- stage windows (coalesced)
-			for (uint32_t i = 0; i < nLists; ++i) {
-				const uint32_t take = min(sh.rem[i], stride);
-				const uint32_t* src = sh.base[i] + sh.cur[i];
-				uint32_t* dst = sh.win + i * stride;
-				for (uint32_t x = tid; x < take; x += FS_THREADS) dst[x] = __ldg(src + x);
-			}
-			__syncthreads();
-			// ---- pass bound b = min over lists of the first element NOT covered; consumed counts; sentinels
-			if (warp == 0) {
-				uint32_t bound = INF;
-				if ((uint32_t)lane < nLists && sh.rem[lane] > wmax) bound = sh.win[lane * stride + wmax];
-				for (int o = 16; o; o >>= 1) bound = min(bound, __shfl_xor_sync(0xffffffffu, bound, o));
-				uint32_t nt = 0, last = 0;
-				if ((uint32_t)lane < nLists) {
-					const uint32_t avail = min(sh.rem[lane], wmax);
-					nt = bound == INF ? avail : lower_bound_smem(sh.win + lane * stride, avail, bound);
-					sh.nTake[lane] = nt;
-					if (nt) last = sh.win[lane * stride + nt - 1];
-					sh.win[lane * stride + nt] = INF;
-				} else if (lane < MAX_QGRAMS) sh.nTake[lane] = 0;
-				uint32_t best = nt;
-				for (int o = 16; o; o >>= 1) {
-					best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-					last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-				}
-				if (lane == 0) {
-					sh.stride = stride;
-					sh.passHi = bound == INF ? last + 1 : bound;
-					uint32_t top = 0;
-					if (best) { top = 1; while ((top << 1) <= best) top <<= 1; }
-					sh.searchTop = top;
-					// integer pre-filter: counts c <= cRej can neither pass the threshold nor beat the running k-th best
-					uint32_t rej = sh.cmin ? sh.cmin - 1 : 0;
-					const unsigned long long tau = sh.tau;
-					for (uint32_t c = rej + 1; c <= nGrams; ++c) {
-						if ((((unsigned long long)sh.hiKey[c]) << 32) >= tau) rej = c; else break;
-					}
-					sh.cRej = rej;
-					if (best == 0) sh.overflow = 2;      // no list can advance (corrupt postings): never spin, fall back
-				}
-			}
-			__syncthreads();
-			if (sh.overflow == 2) { failed = true; break; }
-			// ---- merge
-			if (sh.allOnes) merge_dispatch<U, true>(sh, qn, nLists);
-			else merge_dispatch<U, false>(sh, qn, nLists);
-			__syncthreads();
-			if (sh.overflow) {
-				// the optimistic pass overflowed the candidate buffer: roll it back, make room, redo it with a
-				// window small enough to be safe for single-edge terms; if even that overflows -> dense path
-				if (safeMode && level <= k) { failed = true; break; }
-				__syncthreads();
-				if (tid == 0) { sh.bufCount = level; sh.overflow = 0; }
-				__syncthreads();
-				if (level > k) { select_smallest(sh, level, k); level = k; }
-				safeMode = true;
-				continue;
-			}
-			safeMode = false;
-			firstPass = false;
-			if (tid < MAX_QGRAMS && (uint32_t)tid < nLists) { sh.cur[tid] += sh.nTake[tid]; sh.rem[tid] -= sh.nTake[tid]; }
-			level = sh.bufCount;
-			const uint32_t nextLo = sh.passHi;
-			__syncthreads();
-			if (tid == 0) sh.passLo = nextLo;
-			// establish / tighten tau once enough candidates are buffered
-			if (level > k && (sh.tau == ~0ull || level > FS_BUF / 2)) { select_smallest(sh, level, k); level = k; }
-		}
-		if (failed) {
-			if (tid == 0) {
-				denseList[atomicAdd(&counters[1], 1u)] = q;
-				atomicAdd(&counters[3], 1u);
-			}
-			continue;
-		}
-		// ---- final: top-k, sorted
-		if (level > k) { select_smallest(sh, level, k); level = k; }
-		sort_buffer(sh, level);
-		for (uint32_t i = tid; i < level; i += FS_THREADS) {
-			unsigned long long v = sh.buf[i];
-			outKid[(size_t)q * outStride + i] = (uint32_t)v;
-			outScore[(size_t)q * outStride + i] = rank_key_score(v);
-		}
-		if (tid == 0) {
-			outCount[q] = level;
-			atomicAdd(&statCounters[0], (unsigned long long)d.total);
-		}
-	}
-}
+namespace {
 
 // ---------------------------------------------------------------------------------------------- dense path
 // one CTA per gram window of the query: counts[t] += 1 for every term of the window's posting list (hpp:289-298)
