@@ -20,10 +20,10 @@ namespace {
 
 constexpr uint32_t INF = 0xFFFFFFFFu;
 constexpr int FS_THREADS = 256;
-constexpr int FS_WIN = 16384;                            // posting slots per staged pass
+constexpr int FS_WIN = 12288;                            // posting slots per staged pass
 constexpr int FS_REGION_PAD = 12;                        // per-list slack: 16-byte alignment shift (<=3) + bound slot + rounding
 constexpr int FS_WIN_ALLOC = FS_WIN + MAX_QGRAMS * FS_REGION_PAD + 16;
-constexpr int FS_BUF = 4096;                             // candidate buffer entries (>= 2 * FAST_KLIM)
+constexpr int FS_BUF = 2048;                             // candidate buffer entries (>= 2 * FAST_KLIM)
 constexpr int FS_FIRST_PASS = 2048;                      // small first pass: establishes tau early
 
 struct PassPlan {
@@ -78,6 +78,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 		             : "memory");
 		if (spin > (1u << 24)) __trap();      // a lost TMA completion must never hang the GPU
 	}
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
 }
 
 __device__ __forceinline__ uint32_t lower_bound_smem(const uint32_t* a, uint32_t n, uint32_t x)
@@ -213,30 +220,28 @@ __device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__
 	const uint32_t lo = sh.passLo + (uint32_t)((span * (unsigned)tid) / FS_THREADS);
 	const uint32_t hi = (tid == FS_THREADS - 1) ? sh.passHi : sh.passLo + (uint32_t)((span * (unsigned)(tid + 1)) / FS_THREADS);
 	if (lo >= hi) return;
-	const char* winBytes = reinterpret_cast<const char*>(&sh.win[0]);
-	uint32_t pos[KT], head[KT], mu[ONES ? 1 : KT];       // pos: BYTE offsets from winBytes (one LDS, no address math)
+	const uint32_t winAddr = smem_u32(&sh.win[0]);
+	uint32_t pos[KT], head[KT], mu[ONES ? 1 : KT];       // pos: absolute shared-memory byte addresses (one LDS, no address math)
 	{
-		uint32_t nT[KT], base[KT];
+		uint32_t end[KT];
 #pragma unroll
 		for (int i = 0; i < KT; ++i) {
 			const bool on = (uint32_t)i < nLists;
-			nT[i] = on ? sh.nTake[i] : 0;
-			base[i] = on ? sh.winByte[i] : (uint32_t)((FS_WIN_ALLOC - 1) * 4);       // template slots beyond K read the INF slot
-			pos[i] = 0;
+			// template slots beyond K are empty windows that read the INF slot
+			pos[i] = winAddr + (on ? sh.winByte[i] : (uint32_t)((FS_WIN_ALLOC - 1) * 4));
+			end[i] = pos[i] + (on ? sh.nTake[i] * 4 : 0u);
 			if (!ONES) mu[i] = sh.mult[i];
 		}
-		for (uint32_t st = sh.searchTop; st > 0; st >>= 1) {
+		// lower_bound(lo) in every window: branch-free, all K searches advance in lock step (K independent LDS per step)
+		for (uint32_t st = sh.searchTop * 4; st >= 4; st >>= 1) {
 #pragma unroll
 			for (int i = 0; i < KT; ++i) {
 				const uint32_t q = pos[i] + st;
-				if (q <= nT[i] && *reinterpret_cast<const uint32_t*>(winBytes + base[i] + (q - 1) * 4) < lo) pos[i] = q;
+				if (q <= end[i] && lds_u32(q - 4) < lo) pos[i] = q;
 			}
 		}
 #pragma unroll
-		for (int i = 0; i < KT; ++i) {
-			pos[i] = base[i] + pos[i] * 4;
-			head[i] = *reinterpret_cast<const uint32_t*>(winBytes + pos[i]);
-		}
+		for (int i = 0; i < KT; ++i) head[i] = lds_u32(pos[i]);
 	}
 	const uint32_t cRej = sh.cRej;
 	while (true) {
@@ -250,7 +255,7 @@ __device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__
 			if (head[i] == m) {
 				c += ONES ? 1u : mu[i];
 				pos[i] += 4;
-				head[i] = *reinterpret_cast<const uint32_t*>(winBytes + pos[i]);
+				head[i] = lds_u32(pos[i]);
 			}
 		}
 		if (c > cRej) emit_candidate<U>(sh, qn, m, c);
@@ -321,7 +326,7 @@ __device__ __forceinline__ bool plan_and_issue(FastShared& sh, uint32_t cur, uin
 }
 
 template <class U>
-__global__ void __launch_bounds__(FS_THREADS) k_fast_search(IndexView ix, const QDesc* __restrict__ desc, const U* __restrict__ qnorm,
+__global__ void __launch_bounds__(FS_THREADS, 3) k_fast_search(IndexView ix, const QDesc* __restrict__ desc, const U* __restrict__ qnorm,
                                                             const uint32_t* __restrict__ fastList, uint32_t* __restrict__ counters,
                                                             uint32_t* __restrict__ denseList, uint32_t limit, uint32_t outStride,
                                                             uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
@@ -379,6 +384,19 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_search(IndexView ix, const 
 		bool failed = false, safeMode = false, more = nLists != 0;
 		uint32_t level = 0;
 		uint32_t cap = d.total > FS_FIRST_PASS ? FS_FIRST_PASS : FS_WIN;      // small first pass: it only has to establish tau
+		if (ix.identity && ix.uniformW && d.cmin <= 1 && k <= FAST_KLIM) {
+			// Seed tau without a pass: the first k postings of any one list are k distinct keys (kid == term id) with at least
+			// one match each, i.e. k candidates ranking at or before (score(1), kid = list[k-1]). The final k-th best cannot
+			// be worse, so everything behind the smallest such bound can be dropped from the start.
+			if (warp == 0) {
+				uint32_t x = INF;
+				if ((uint32_t)lane < nLists && d.listLen[lane] >= k) x = __ldg(ix.postings + d.listOff[lane] + (k - 1));
+				for (int o = 16; o; o >>= 1) x = min(x, __shfl_xor_sync(0xffffffffu, x, o));
+				if (lane == 0 && x != INF) sh.tau = ((((unsigned long long)sh.exactKey[1]) << 32) | x) + 1;   // "< tau" keeps the bound itself
+			}
+			__syncthreads();
+			if (sh.tau != ~0ull) cap = FS_WIN;
+		}
 		while (more) {
 			// ---- warp 0: lay out the windows from the cursors and issue the TMA copies
 			if (warp == 0) {
@@ -458,8 +476,9 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_search(IndexView ix, const 
 			const uint32_t nextLo = sh.passHi;
 			__syncthreads();
 			if (tid == 0) sh.passLo = nextLo;
-			// establish tau as soon as k candidates exist, tighten it whenever the buffer grew by half of k again
-			if (level > k && (sh.tau == ~0ull || level >= k + (k >> 1) + 32 || level > FS_BUF / 2)) { select_smallest(sh, level, k); level = k; }
+			// establish tau as soon as k candidates exist; afterwards the exact integer pre-filter keeps appends rare, so the
+			// (barrier-heavy) select only runs again when the buffer is half full
+			if (level > k && (sh.tau == ~0ull || level > FS_BUF / 2)) { select_smallest(sh, level, k); level = k; }
 		}
 		if (failed) {
 			if (tid == 0) {
