@@ -19,11 +19,11 @@
 namespace {
 
 constexpr uint32_t INF = 0xFFFFFFFFu;
-constexpr int FS_THREADS = 256;
-constexpr int FS_WIN = 12288;                            // posting slots per staged pass
+constexpr int FS_THREADS = 128;
+constexpr int FS_WIN = 6144;                            // posting slots per staged pass
 constexpr int FS_REGION_PAD = 12;                        // per-list slack: 16-byte alignment shift (<=3) + bound slot + rounding
 constexpr int FS_WIN_ALLOC = FS_WIN + MAX_QGRAMS * FS_REGION_PAD + 16;
-constexpr int FS_BUF = 2048;                             // candidate buffer entries (>= 2 * FAST_KLIM)
+constexpr int FS_BUF_MAX = 2 * FAST_KLIM;                // candidate buffer entries: 2 * limit rounded up to a power of two, chosen at launch
 constexpr int FS_FIRST_PASS = 2048;                      // small first pass: establishes tau early
 
 struct PassPlan {
@@ -35,7 +35,8 @@ struct PassPlan {
 
 struct FastShared {
 	alignas(16) uint32_t win[FS_WIN_ALLOC];
-	alignas(16) unsigned long long buf[FS_BUF];
+	unsigned long long* buf;                            // candidate buffer: bufCap entries behind this struct in dynamic smem
+	uint32_t bufCap;
 	alignas(8) unsigned long long bar;                  // mbarrier of the stage buffer (TMA completion)
 	uint32_t hist[256];
 	PassPlan plan;
@@ -104,7 +105,7 @@ __device__ void select_smallest(FastShared& sh, uint32_t n, uint32_t k)
 	unsigned long long prefix = 0;
 	uint32_t kk = k;
 	for (int shift = 56; shift >= 0; shift -= 8) {
-		sh.hist[tid] = 0;
+		for (int i = tid; i < 256; i += FS_THREADS) sh.hist[i] = 0;
 		__syncthreads();
 		for (uint32_t i = tid; i < n; i += FS_THREADS) {
 			unsigned long long v = sh.buf[i];
@@ -132,7 +133,7 @@ __device__ void select_smallest(FastShared& sh, uint32_t n, uint32_t k)
 		prefix = (prefix << 8) | sh.selPrefixLo;
 		kk = sh.selK;
 	}
-	unsigned long long keep[FS_BUF / FS_THREADS];
+	unsigned long long keep[FS_BUF_MAX / FS_THREADS];
 	uint32_t nk = 0;
 	for (uint32_t i = tid; i < n; i += FS_THREADS) {
 		unsigned long long v = sh.buf[i];
@@ -144,7 +145,7 @@ __device__ void select_smallest(FastShared& sh, uint32_t n, uint32_t k)
 	__syncthreads();
 }
 
-// ascending bitonic sort of buf[0..n), n <= FS_BUF. CTA-wide.
+// ascending bitonic sort of buf[0..n), n <= bufCap. CTA-wide.
 __device__ void sort_buffer(FastShared& sh, uint32_t n)
 {
 	uint32_t p = 1;
@@ -179,7 +180,7 @@ __device__ __noinline__ void emit_candidate(FastShared& sh, const U* __restrict_
 		const unsigned long long key = ((unsigned long long)hk << 32) | kid;
 		if (key < tau) {
 			uint32_t idx = atomicAdd(&sh.bufCount, 1u);
-			if (idx < FS_BUF) sh.buf[idx] = key; else sh.overflow = 1;
+			if (idx < sh.bufCap) sh.buf[idx] = key; else sh.overflow = 1;
 		}
 		return;
 	}
@@ -207,7 +208,7 @@ __device__ __noinline__ void emit_candidate(FastShared& sh, const U* __restrict_
 		}
 		if (dominated) continue;
 		uint32_t idx = atomicAdd(&sh.bufCount, 1u);
-		if (idx < FS_BUF) sh.buf[idx] = key; else sh.overflow = 1;
+		if (idx < sh.bufCap) sh.buf[idx] = key; else sh.overflow = 1;
 	}
 }
 
@@ -326,11 +327,12 @@ __device__ __forceinline__ bool plan_and_issue(FastShared& sh, uint32_t cur, uin
 }
 
 template <class U>
-__global__ void __launch_bounds__(FS_THREADS, 3) k_fast_search(IndexView ix, const QDesc* __restrict__ desc, const U* __restrict__ qnorm,
+__global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, const QDesc* __restrict__ desc, const U* __restrict__ qnorm,
                                                             const uint32_t* __restrict__ fastList, uint32_t* __restrict__ counters,
                                                             uint32_t* __restrict__ denseList, uint32_t limit, uint32_t outStride,
                                                             uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
-                                                            float* __restrict__ outScore, unsigned long long* __restrict__ statCounters)
+                                                            float* __restrict__ outScore, unsigned long long* __restrict__ statCounters,
+                                                            uint32_t bufCap)
 {
 	extern __shared__ __align__(16) unsigned char fs_smem[];
 	FastShared& sh = *reinterpret_cast<FastShared*>(fs_smem);
@@ -340,6 +342,8 @@ __global__ void __launch_bounds__(FS_THREADS, 3) k_fast_search(IndexView ix, con
 	if (tid == 0) {
 		sh.win[FS_WIN_ALLOC - 1] = INF;
 		sh.ix = ix;
+		sh.buf = reinterpret_cast<unsigned long long*>(fs_smem + ((sizeof(FastShared) + 15) & ~size_t(15)));
+		sh.bufCap = bufCap;
 		mbar_init(&sh.bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(FS_THREADS, 3) k_fast_search(IndexView ix, con
 				__syncthreads();
 				if (level > k) { select_smallest(sh, level, k); level = k; }
 				safeMode = true;
-				cap = min((uint32_t)FS_WIN, (uint32_t)FS_BUF - level);
+				cap = min((uint32_t)FS_WIN, bufCap - level);
 				continue;
 			}
 			safeMode = false;
@@ -478,7 +482,7 @@ __global__ void __launch_bounds__(FS_THREADS, 3) k_fast_search(IndexView ix, con
 			if (tid == 0) sh.passLo = nextLo;
 			// establish tau as soon as k candidates exist; afterwards the exact integer pre-filter keeps appends rare, so the
 			// (barrier-heavy) select only runs again when the buffer is half full
-			if (level > k && (sh.tau == ~0ull || level > FS_BUF / 2)) { select_smallest(sh, level, k); level = k; }
+			if (level > k && (sh.tau == ~0ull || level > bufCap / 2)) { select_smallest(sh, level, k); level = k; }
 		}
 		if (failed) {
 			if (tid == 0) {

@@ -458,17 +458,27 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
                 BatchOutput* out, cudaStream_t s, SearchStats* st)
 {
 	const IndexView v = make_view(ix);
-	static int numSMs = 0, ctasPerSM = 1;
-	static size_t smemBytes = sizeof(FastShared);
+	// candidate buffer: 2 * limit entries rounded up to a power of two (>= 1024); it decides the CTA's shared memory
+	// footprint and with it the number of resident CTAs per SM (6 x 128 threads at limit <= 512)
+	uint32_t bufCap = 1024;
+	while (bufCap < 2 * std::min<uint32_t>(limit, FAST_KLIM)) bufCap <<= 1;
+	const size_t smemBytes = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)bufCap * 8;
+	static int numSMs = 0;
+	static int ctasFor[3] = {0, 0, 0};
+	const int cfg = bufCap == 1024 ? 0 : (bufCap == 2048 ? 1 : 2);
 	if (!numSMs) {
 		int dev = 0;
 		SSB_CUDA(cudaGetDevice(&dev));
 		SSB_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
-		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_fast_search<U>, FS_THREADS, smemBytes));
-		if (ctasPerSM < 1) ctasPerSM = 1;
+		const int maxSmem = (int)(((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)FS_BUF_MAX * 8);
+		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
 	}
+	if (!ctasFor[cfg]) {
+		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasFor[cfg], k_fast_search<U>, FS_THREADS, smemBytes));
+		if (ctasFor[cfg] < 1) ctasFor[cfg] = 1;
+	}
+	const int ctasPerSM = ctasFor[cfg];
 	SSB_CUDA(cudaEventRecord(ws.ev0, s));
 	ws.counters.zero(s);
 	ws.statCounters.zero(s);
@@ -483,7 +493,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	const unsigned grid = (unsigned)std::min<size_t>((size_t)numSMs * ctasPerSM, std::max<uint32_t>(nq, 1));
 	k_fast_search<U><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(), ws.denseList.get(),
 	                                                     limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(),
-	                                                     ws.statCounters.get());
+	                                                     ws.statCounters.get(), bufCap);
 	SSB_LAUNCH_CHECK();
 	SSB_CUDA(cudaEventRecord(ws.ev2, s));
 	uint32_t hc[4];

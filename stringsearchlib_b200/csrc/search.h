@@ -7,7 +7,7 @@
 namespace ssb {
 
 constexpr int MAX_QGRAMS = 32;      // fast path: at most 32 gram windows per query (longer queries take the dense path)
-constexpr int FAST_KLIM = 1024;     // fast path: limit <= FAST_KLIM
+constexpr int FAST_KLIM = 2048;     // fast path: limit <= FAST_KLIM
 
 enum QueryClass : uint32_t { QC_EMPTY = 0, QC_FAST = 1, QC_DENSE = 2, QC_WILDCARD = 3 };
 
