@@ -153,7 +153,8 @@ def main():
     workload = f"C4: {args.keys}-key synthetic ASCII vocabulary (6-16 letters), rowSize=1, gSize=3, batch {args.batch}, " \
                f"threshold {args.threshold:g}, top-{args.limit}"
     config = {"workload": workload, "keys": args.keys, "batch": args.batch, "limit": args.limit, "threshold": args.threshold,
-              "gSize": 3, "rowSize": 1, "sharding": f"key-range x{world}" if world > 1 else "single shard",
+              "gSize": 3, "rowSize": 1,
+              "sharding": f"key-range x{world}; all-to-all + merge + all-gather of per-query records (NCCL)" if world > 1 else "single shard",
               "l2": "inputs larger than L2: new query batch every step, ~184 KB of postings per query"}
 
     if args.impl == "reference":
@@ -220,17 +221,32 @@ def main():
     batches = [synth.ascii_queries(args.batch, args.keys, first_query=s * args.batch) for s in range(nsteps)]
     qptrs = [b.pointers() for b in batches]
     rec_bytes = RECORD_DTYPE.itemsize
+    sliced = world > 1 and args.batch % world == 0
     if world > 1:
         mine = torch.empty((args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
-        gathered = torch.empty((world, args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
         merged = torch.empty((args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
         mcount = torch.empty(args.batch, dtype=torch.int32, device="cuda")
+        if sliced:
+            part_q = args.batch // world
+            recv = torch.empty((world, part_q, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
+            part = torch.empty((part_q, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
+            pcount = torch.empty(part_q, dtype=torch.int32, device="cuda")
+        else:
+            gathered = torch.empty((world, args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
 
     def exchange():
+        """per-query top-k merge across the key-range shards. Every rank merges a 1/N slice of the queries: all-to-all of the
+        fixed-size records, merge kernel, all-gather of the merged slices (NCCL over NVLink; all ranks end with all results).
+        The engine calls synchronise their own stream; the merge kernel runs on the default stream behind the collectives."""
         ix.export_records(args.batch, args.limit, mine.data_ptr())
-        dist.all_gather_into_tensor(gathered, mine)
-        torch.cuda.synchronize()
-        merge_records(gathered.data_ptr(), world, args.batch, args.limit, merged.data_ptr(), mcount.data_ptr())
+        if sliced:
+            dist.all_to_all_single(recv, mine)
+            merge_records(recv.data_ptr(), world, part_q, args.limit, part.data_ptr(), pcount.data_ptr())
+            dist.all_gather_into_tensor(merged, part)
+            dist.all_gather_into_tensor(mcount, pcount)
+        else:
+            dist.all_gather_into_tensor(gathered, mine)
+            merge_records(gathered.data_ptr(), world, args.batch, args.limit, merged.data_ptr(), mcount.data_ptr())
 
     dev_ms, fast_ms, e2e_s, step_s, postings, results = [], [], [], [], [], []
     sampler = ClockSampler(local_rank)

@@ -494,8 +494,8 @@ SSB_API int ssb_merge_records(const void* d_gathered, uint32_t nShards, uint32_t
 {
 	return guarded([&] {
 		g_engine.init();
+		// asynchronous on the legacy default stream: ordered behind collectives the caller enqueued there (torch's default)
 		merge_records(static_cast<const MergeRecord*>(d_gathered), nShards, nq, limit, static_cast<MergeRecord*>(d_merged), d_counts, 0);
-		SSB_CUDA(cudaStreamSynchronize(0));
 		return 0;
 	}, -1);
 }

@@ -205,6 +205,38 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 
 namespace {
 
+// Longest-processing-time-first order of the fast queries: with only a handful of queries per persistent CTA the tail of
+// a batch is set by whichever long query starts last; sorting by posting volume (descending) starts the long ones first.
+// One CTA, bitonic sort of (~total, query) in shared memory; batches above ORDER_MAX queries are left as they are.
+constexpr uint32_t ORDER_MAX = 8192;
+__global__ void __launch_bounds__(1024) k_order_fast(const QDesc* __restrict__ desc, uint32_t* __restrict__ fastList,
+                                                     const uint32_t* __restrict__ counters)
+{
+	extern __shared__ __align__(16) unsigned char order_smem[];
+	unsigned long long* key = reinterpret_cast<unsigned long long*>(order_smem);
+	const uint32_t n = counters[0];
+	if (n < 2 || n > ORDER_MAX) return;
+	uint32_t p = 2;
+	while (p < n) p <<= 1;
+	for (uint32_t i = threadIdx.x; i < p; i += blockDim.x) {
+		unsigned long long k = ~0ull;
+		if (i < n) { const uint32_t q = fastList[i]; k = ((unsigned long long)(~desc[q].total) << 32) | q; }
+		key[i] = k;
+	}
+	__syncthreads();
+	for (uint32_t size = 2; size <= p; size <<= 1)
+		for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+			for (uint32_t i = threadIdx.x; i < (p >> 1); i += blockDim.x) {
+				uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+				bool up = (lo & size) == 0;
+				unsigned long long a = key[lo], b = key[hi];
+				if ((a > b) == up) { key[lo] = b; key[hi] = a; }
+			}
+			__syncthreads();
+		}
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) fastList[i] = (uint32_t)key[i];
+}
+
 // ---------------------------------------------------------------------------------------------- dense path
 // one CTA per gram window of the query: counts[t] += 1 for every term of the window's posting list (hpp:289-298)
 template <class U>
@@ -488,6 +520,15 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	                                                          ws.fastList.get(), ws.denseList.get(), ws.counters.get(),
 	                                                          ws.outCount.get());
 	SSB_LAUNCH_CHECK();
+	if (nq <= ORDER_MAX) {
+		static bool orderAttr = false;
+		if (!orderAttr) {
+			SSB_CUDA(cudaFuncSetAttribute(k_order_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ORDER_MAX * 8)));
+			orderAttr = true;
+		}
+		k_order_fast<<<1, 1024, ORDER_MAX * 8, s>>>(ws.desc.get(), ws.fastList.get(), ws.counters.get());
+		SSB_LAUNCH_CHECK();
+	}
 	SSB_CUDA(cudaEventRecord(ws.ev1, s));
 	// persistent grid: one wave of resident CTAs (148 SMs x occupancy), queries handed out by an atomic cursor
 	const unsigned grid = (unsigned)std::min<size_t>((size_t)numSMs * ctasPerSM, std::max<uint32_t>(nq, 1));
