@@ -244,19 +244,44 @@ __device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__
 #pragma unroll
 		for (int i = 0; i < KT; ++i) head[i] = lds_u32(pos[i]);
 	}
-	const uint32_t cRej = sh.cRej;
+	// integer pre-filter, refined per thread in identity mode: every kid of this slice is >= lo, so a whole score class
+	// that ties with tau but lies behind tau's kid can be rejected without evaluating its candidates
+	uint32_t cRej = sh.cRej;
+	if (sh.ix.identity && sh.ix.uniformW) {
+		const unsigned long long tau = sh.tau;
+		const uint32_t nG = sh.nGrams;
+		while (cRej < nG && ((((unsigned long long)sh.hiKey[cRej + 1]) << 32) | lo) >= tau) ++cRej;
+	}
 	while (true) {
 		uint32_t m = head[0];
 #pragma unroll
 		for (int i = 1; i < KT; ++i) m = min(m, head[i]);
 		if (m >= hi) break;
 		uint32_t c = 0;
+		if (ONES) {
+			// count = number of cursors that advance = (sum of cursor addresses after - before) / 4: the adds fold into
+			// 3-input IADD3s, cheaper than one predicated increment per list
+			uint32_t before = 0, after = 0;
 #pragma unroll
-		for (int i = 0; i < KT; ++i) {
-			if (head[i] == m) {
-				c += ONES ? 1u : mu[i];
-				pos[i] += 4;
-				head[i] = lds_u32(pos[i]);
+			for (int i = 0; i < KT; ++i) before += pos[i];
+#pragma unroll
+			for (int i = 0; i < KT; ++i) {
+				if (head[i] == m) {
+					pos[i] += 4;
+					head[i] = lds_u32(pos[i]);
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < KT; ++i) after += pos[i];
+			c = (after - before) >> 2;
+		} else {
+#pragma unroll
+			for (int i = 0; i < KT; ++i) {
+				if (head[i] == m) {
+					c += mu[i];
+					pos[i] += 4;
+					head[i] = lds_u32(pos[i]);
+				}
 			}
 		}
 		if (c > cRej) emit_candidate<U>(sh, qn, m, c);

@@ -206,35 +206,51 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 namespace {
 
 // Longest-processing-time-first order of the fast queries: with only a handful of queries per persistent CTA the tail of
-// a batch is set by whichever long query starts last; sorting by posting volume (descending) starts the long ones first.
-// One CTA, bitonic sort of (~total, query) in shared memory; batches above ORDER_MAX queries are left as they are.
-constexpr uint32_t ORDER_MAX = 8192;
+// a batch is set by whichever long query starts last; starting the heavy ones first shortens it. An exact order is not
+// needed: one CTA does a 256-bin counting sort by posting volume (descending); larger batches are left as they are.
+constexpr uint32_t ORDER_MAX = 16384;
 __global__ void __launch_bounds__(1024) k_order_fast(const QDesc* __restrict__ desc, uint32_t* __restrict__ fastList,
                                                      const uint32_t* __restrict__ counters)
 {
 	extern __shared__ __align__(16) unsigned char order_smem[];
-	unsigned long long* key = reinterpret_cast<unsigned long long*>(order_smem);
+	uint32_t* qs = reinterpret_cast<uint32_t*>(order_smem);          // [ORDER_MAX] query ids
+	uint32_t* bins = qs + ORDER_MAX;                                 // [ORDER_MAX] bin of each entry
+	__shared__ uint32_t hist[256], maxTotal;
 	const uint32_t n = counters[0];
 	if (n < 2 || n > ORDER_MAX) return;
-	uint32_t p = 2;
-	while (p < n) p <<= 1;
-	for (uint32_t i = threadIdx.x; i < p; i += blockDim.x) {
-		unsigned long long k = ~0ull;
-		if (i < n) { const uint32_t q = fastList[i]; k = ((unsigned long long)(~desc[q].total) << 32) | q; }
-		key[i] = k;
+	if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+	if (threadIdx.x == 0) maxTotal = 0;
+	__syncthreads();
+	uint32_t localMax = 0;
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+		const uint32_t q = fastList[i];
+		qs[i] = q;
+		bins[i] = desc[q].total;
+		localMax = max(localMax, bins[i]);
+	}
+	for (int o = 16; o; o >>= 1) localMax = max(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
+	if ((threadIdx.x & 31) == 0) atomicMax(&maxTotal, localMax);
+	__syncthreads();
+	const uint32_t div = maxTotal / 255 + 1;
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+		const uint32_t b = 255 - bins[i] / div;                      // heavy queries -> low bins -> first
+		bins[i] = b;
+		atomicAdd(&hist[b], 1u);
 	}
 	__syncthreads();
-	for (uint32_t size = 2; size <= p; size <<= 1)
-		for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-			for (uint32_t i = threadIdx.x; i < (p >> 1); i += blockDim.x) {
-				uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
-				bool up = (lo & size) == 0;
-				unsigned long long a = key[lo], b = key[hi];
-				if ((a > b) == up) { key[lo] = b; key[hi] = a; }
-			}
-			__syncthreads();
-		}
-	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) fastList[i] = (uint32_t)key[i];
+	if (threadIdx.x < 32) {                                          // exclusive scan of 256 bins by one warp
+		uint32_t loc[8], sum = 0;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) { loc[j] = hist[threadIdx.x * 8 + j]; sum += loc[j]; }
+		uint32_t inc = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (threadIdx.x >= o) inc += t; }
+		uint32_t run = inc - sum;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) { hist[threadIdx.x * 8 + j] = run; run += loc[j]; }
+	}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) fastList[atomicAdd(&hist[bins[i]], 1u)] = qs[i];
 }
 
 // ---------------------------------------------------------------------------------------------- dense path
