@@ -144,6 +144,8 @@ def main():
     ap.add_argument("--cpu-keys", type=int, default=1_000_000, help="vocabulary prefix indexed by the CPU reference leg")
     ap.add_argument("--cpu-queries", type=int, default=256, help="queries per step of the CPU reference leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: fused export/merge kernels storing into NVLink peer memory (default) or NCCL all-to-all + all-gather")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -154,7 +156,7 @@ def main():
                f"threshold {args.threshold:g}, top-{args.limit}"
     config = {"workload": workload, "keys": args.keys, "batch": args.batch, "limit": args.limit, "threshold": args.threshold,
               "gSize": 3, "rowSize": 1,
-              "sharding": f"key-range x{world}; all-to-all + merge + all-gather of per-query records (NCCL)" if world > 1 else "single shard",
+              "sharding": f"key-range x{world}; per-query top-k merge, exchange={args.exchange}" if world > 1 else "single shard",
               "l2": "inputs larger than L2: new query batch every step, ~184 KB of postings per query"}
 
     if args.impl == "reference":
@@ -176,6 +178,7 @@ def main():
     import torch
     import stringsearchlib_b200 as ssb
     from stringsearchlib_b200 import synth
+    from stringsearchlib_b200 import api
     from stringsearchlib_b200.api import RECORD_DTYPE, merge_records
 
     torch.cuda.set_device(local_rank)
@@ -222,12 +225,33 @@ def main():
     qptrs = [b.pointers() for b in batches]
     rec_bytes = RECORD_DTYPE.itemsize
     sliced = world > 1 and args.batch % world == 0
+    use_p2p = sliced and args.exchange == "p2p"
     if world > 1:
+        part_q = args.batch // world if sliced else 0
+        host_rec = torch.empty((args.batch, args.limit, rec_bytes), dtype=torch.uint8, pin_memory=True)
+        host_cnt = torch.empty(args.batch, dtype=torch.int32, pin_memory=True)
+        flag = torch.zeros(1, device="cuda")
+    if use_p2p:
+        # result / receive buffers are cudaMalloc'ed by the engine and opened in every peer process through CUDA IPC
+        recv_ptr = api.device_alloc(world * part_q * args.limit * rec_bytes)
+        merged_ptr = api.device_alloc(args.batch * args.limit * rec_bytes)
+        counts_ptr = api.device_alloc(args.batch * 4)
+        handles = [None] * world
+        dist.all_gather_object(handles, tuple(api.ipc_get_handle(p) for p in (recv_ptr, merged_ptr, counts_ptr)))
+        try:
+            peer_recv = [recv_ptr if r == rank else api.ipc_open_handle(handles[r][0]) for r in range(world)]
+            peer_merged = [merged_ptr if r == rank else api.ipc_open_handle(handles[r][1]) for r in range(world)]
+            peer_counts = [counts_ptr if r == rank else api.ipc_open_handle(handles[r][2]) for r in range(world)]
+            ok = torch.ones(1, device="cuda")
+        except RuntimeError:
+            ok = torch.zeros(1, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        use_p2p = bool(ok.item() > 0)
+    if world > 1 and not use_p2p:
         mine = torch.empty((args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
         merged = torch.empty((args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
         mcount = torch.empty(args.batch, dtype=torch.int32, device="cuda")
         if sliced:
-            part_q = args.batch // world
             recv = torch.empty((world, part_q, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
             part = torch.empty((part_q, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
             pcount = torch.empty(part_q, dtype=torch.int32, device="cuda")
@@ -235,9 +259,19 @@ def main():
             gathered = torch.empty((world, args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
 
     def exchange():
-        """per-query top-k merge across the key-range shards. Every rank merges a 1/N slice of the queries: all-to-all of the
-        fixed-size records, merge kernel, all-gather of the merged slices (NCCL over NVLink; all ranks end with all results).
-        The engine calls synchronise their own stream; the merge kernel runs on the default stream behind the collectives."""
+        """per-query top-k merge across the key-range shards; every rank merges a 1/N slice of the queries.
+        p2p : the export kernel stores each record into the merging rank's buffer over NVLink, the merge kernel stores its
+              slice of final records into every rank's result buffer; the only collectives are two 4-byte all-reduces that
+              act as cross-rank barriers.
+        nccl: all-to-all of the records, merge kernel, all-gather of the merged slices."""
+        if use_p2p:
+            ix.export_records_p2p(args.batch, args.limit, peer_recv, rank)
+            dist.all_reduce(flag)
+            torch.cuda.synchronize()
+            api.merge_records_p2p(recv_ptr, world, part_q, args.limit, peer_merged, peer_counts, rank)
+            dist.all_reduce(flag)
+            torch.cuda.synchronize()
+            return
         ix.export_records(args.batch, args.limit, mine.data_ptr())
         if sliced:
             dist.all_to_all_single(recv, mine)
@@ -247,6 +281,15 @@ def main():
         else:
             dist.all_gather_into_tensor(gathered, mine)
             merge_records(gathered.data_ptr(), world, args.batch, args.limit, merged.data_ptr(), mcount.data_ptr())
+
+    def results_to_host():
+        if use_p2p:
+            api.memcpy_d2h(host_rec.numpy(), merged_ptr)
+            api.memcpy_d2h(host_cnt.numpy(), counts_ptr)
+        else:
+            host_rec.copy_(merged, non_blocking=True)
+            host_cnt.copy_(mcount, non_blocking=True)
+            torch.cuda.synchronize()
 
     dev_ms, fast_ms, e2e_s, step_s, postings, results = [], [], [], [], [], []
     sampler = ClockSampler(local_rank)
@@ -267,8 +310,7 @@ def main():
         ix.free_raw(bp)
         if world > 1:
             exchange()
-            host_rec = merged.cpu()
-            host_cnt = mcount.cpu()
+            results_to_host()
         t1 = time.perf_counter()
         # (2) device part only, the same batch resident in HBM
         barrier()

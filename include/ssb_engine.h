@@ -71,6 +71,22 @@ int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uint32_t li
 int ssb_export_records(ssb_index* ix, uint32_t nq, uint32_t limit, void* d_out);
 int ssb_merge_records(const void* d_gathered, uint32_t nShards, uint32_t nq, uint32_t limit, void* d_merged, uint32_t* d_counts);
 
+/* Fused exchange over NVLink peer memory (no collective on the data path): rank r merges queries [r*nq/N, (r+1)*nq/N).
+ * ssb_export_records_p2p stores the records of query q directly into the receive buffer of the rank that merges it
+ * (peerRecv[j]: [N][nq/N][limit] records on rank j); after a cross-rank barrier ssb_merge_records_p2p merges the local
+ * slice and stores the final records / counts into every rank's result buffers (peerMerged[j]: [nq][limit], peerCounts[j]:
+ * [nq] u32); a second barrier makes them visible. Buffers come from ssb_device_alloc (cudaMalloc, IPC-shareable) and are
+ * opened in the other processes with ssb_ipc_get_handle / ssb_ipc_open_handle. nq % N == 0, N <= 16. */
+void* ssb_device_alloc(uint64_t bytes);
+void ssb_device_free(void* d_ptr);
+int ssb_memcpy_d2h(void* dst, const void* d_src, uint64_t bytes);
+int ssb_ipc_get_handle(void* d_ptr, unsigned char handle[64]);
+void* ssb_ipc_open_handle(const unsigned char handle[64]);
+int ssb_ipc_close_handle(void* d_ptr);
+int ssb_export_records_p2p(ssb_index* ix, uint32_t nq, uint32_t limit, void* const* peerRecv, uint32_t nRanks, uint32_t myRank);
+int ssb_merge_records_p2p(const void* d_recv, uint32_t nShards, uint32_t nqLocal, uint32_t limit, void* const* peerMerged,
+                          void* const* peerCounts, uint32_t nRanks, uint32_t myRank);
+
 #ifdef __cplusplus
 }
 #endif

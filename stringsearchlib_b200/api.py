@@ -61,6 +61,16 @@ def core_library():
     lib.ssb_search_resident.argtypes = [c_void_p, c_uint32, c_float, c_uint32, POINTER(c_float), POINTER(c_uint64)]
     lib.ssb_export_records.argtypes = [c_void_p, c_uint32, c_uint32, c_void_p]
     lib.ssb_merge_records.argtypes = [c_void_p, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p]
+    lib.ssb_device_alloc.restype = c_void_p
+    lib.ssb_device_alloc.argtypes = [c_uint64]
+    lib.ssb_device_free.argtypes = [c_void_p]
+    lib.ssb_memcpy_d2h.argtypes = [c_void_p, c_void_p, c_uint64]
+    lib.ssb_ipc_get_handle.argtypes = [c_void_p, c_char_p]
+    lib.ssb_ipc_open_handle.restype = c_void_p
+    lib.ssb_ipc_open_handle.argtypes = [c_char_p]
+    lib.ssb_ipc_close_handle.argtypes = [c_void_p]
+    lib.ssb_export_records_p2p.argtypes = [c_void_p, c_uint32, c_uint32, POINTER(c_void_p), c_uint32, c_uint32]
+    lib.ssb_merge_records_p2p.argtypes = [c_void_p, c_uint32, c_uint32, c_uint32, POINTER(c_void_p), POINTER(c_void_p), c_uint32, c_uint32]
     lib._ssb_typed = True
     return lib
 
@@ -281,9 +291,57 @@ class Index:
             raise RuntimeError(self._lib.ssb_last_error().decode())
         return ms[0], ms[1], dict(nFast=int(st[0]), nDense=int(st[1]), nOverflow=int(st[2]), postings=int(st[3]))
 
+    def export_records_p2p(self, nq, limit, peer_recv, rank):
+        """fused export + exchange: query q's records go straight into peer_recv[q // (nq/N)] (peer-mapped pointers)."""
+        _check(self._lib.ssb_export_records_p2p(self._h, nq, limit, _ptr_list(peer_recv), len(peer_recv), rank))
+
     def export_records(self, nq, limit, device_ptr):
         if self._lib.ssb_export_records(self._h, nq, limit, device_ptr) != 0:
             raise RuntimeError(self._lib.ssb_last_error().decode())
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(core_library().ssb_last_error().decode())
+
+
+def device_alloc(nbytes):
+    """cudaMalloc'ed (IPC-shareable) device buffer, filled with 0xFF; returns the device address."""
+    p = core_library().ssb_device_alloc(int(nbytes))
+    if not p:
+        raise RuntimeError(core_library().ssb_last_error().decode())
+    return int(p)
+
+
+def device_free(ptr):
+    core_library().ssb_device_free(ptr)
+
+
+def memcpy_d2h(dst_array, ptr, nbytes=None):
+    _check(core_library().ssb_memcpy_d2h(dst_array.ctypes.data, ptr, int(nbytes if nbytes is not None else dst_array.nbytes)))
+
+
+def ipc_get_handle(ptr):
+    buf = ctypes.create_string_buffer(64)
+    _check(core_library().ssb_ipc_get_handle(ptr, buf))
+    return buf.raw
+
+
+def ipc_open_handle(handle):
+    p = core_library().ssb_ipc_open_handle(handle)
+    if not p:
+        raise RuntimeError(core_library().ssb_last_error().decode())
+    return int(p)
+
+
+def _ptr_list(ptrs):
+    return (c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def merge_records_p2p(recv_ptr, n_shards, nq_local, limit, peer_merged, peer_counts, rank):
+    """merges this rank's slice of queries and stores the result into every rank's buffers (peer-mapped pointers)."""
+    _check(core_library().ssb_merge_records_p2p(recv_ptr, n_shards, nq_local, limit, _ptr_list(peer_merged), _ptr_list(peer_counts),
+                                                len(peer_merged), rank))
 
 
 def merge_records(gathered_ptr, n_shards, nq, limit, merged_ptr, counts_ptr):

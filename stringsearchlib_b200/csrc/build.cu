@@ -297,16 +297,18 @@ __global__ void k_copy_terms(const U* __restrict__ chars, const uint8_t* __restr
 template <class U>
 __global__ void k_copy_keys(const U* __restrict__ chars, const uint32_t* __restrict__ kidRowLocal, const uint64_t* __restrict__ rowKeyBeg,
                             const uint32_t* __restrict__ keyOff, uint32_t K, uint64_t rowBase, U* __restrict__ out,
-                            uint64_t* __restrict__ keyRow)
+                            uint64_t* __restrict__ keyRow, uint64_t* __restrict__ keyHash)
 {
 	uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= K) return;
 	uint32_t r = kidRowLocal[k];
 	const U* src = chars + rowKeyBeg[r];
 	uint32_t b = keyOff[k], len = keyOff[k + 1] - b - 1;
-	for (uint32_t j = 0; j < len; ++j) out[b + j] = src[j];
+	uint64_t h = 0x6b657973ull;                         // fixed seed: equal key strings hash equally in every shard
+	for (uint32_t j = 0; j < len; ++j) { out[b + j] = src[j]; h = hash_step(h, (uint32_t)src[j]); }
 	out[b + len] = 0;
 	keyRow[k] = rowBase + r;
+	keyHash[k] = hash_done(h, len);
 }
 __global__ void k_compact_short(const uint8_t* __restrict__ isShort, const uint32_t* __restrict__ pos, uint32_t T, uint32_t* __restrict__ out)
 {
@@ -643,11 +645,12 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 	ix.termChars.alloc(std::max<size_t>((size_t)termUnits * sizeof(U), 4), s);
 	ix.keyChars.alloc((size_t)keyUnits * sizeof(U), s);
 	ix.keyRow.alloc(K, s);
+	ix.keyHash.alloc(K, s);
 	k_copy_terms<U><<<grid_for(T), TPB, 0, s>>>(chars.get(), ix.validLut.get(), termWord.get(), termBeg.get(), ix.termOff.get(), T,
 	                                            reinterpret_cast<U*>(ix.termChars.get()));
 	SSB_LAUNCH_CHECK();
 	k_copy_keys<U><<<grid_for(K), TPB, 0, s>>>(chars.get(), kidRowLocal.get(), rowKeyBeg.get(), ix.keyOff.get(), K, rowBase,
-	                                           reinterpret_cast<U*>(ix.keyChars.get()), ix.keyRow.get());
+	                                           reinterpret_cast<U*>(ix.keyChars.get()), ix.keyRow.get(), ix.keyHash.get());
 	SSB_LAUNCH_CHECK();
 	// short terms list (hpp:82-85)
 	{

@@ -500,4 +500,65 @@ SSB_API int ssb_merge_records(const void* d_gathered, uint32_t nShards, uint32_t
 	}, -1);
 }
 
+SSB_API void* ssb_device_alloc(uint64_t bytes)
+{
+	return guarded([&]() -> void* {
+		g_engine.init();
+		void* p = nullptr;
+		SSB_CUDA(cudaMalloc(&p, bytes));
+		SSB_CUDA(cudaMemset(p, 0xFF, bytes));
+		return p;
+	}, nullptr);
+}
+SSB_API void ssb_device_free(void* d_ptr) { if (d_ptr) cudaFree(d_ptr); }
+SSB_API int ssb_memcpy_d2h(void* dst, const void* d_src, uint64_t bytes)
+{
+	return guarded([&] { g_engine.init(); SSB_CUDA(cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost)); return 0; }, -1);
+}
+SSB_API int ssb_ipc_get_handle(void* d_ptr, unsigned char handle[64])
+{
+	return guarded([&] {
+		g_engine.init();
+		static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+		cudaIpcMemHandle_t h;
+		SSB_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+		memcpy(handle, &h, 64);
+		return 0;
+	}, -1);
+}
+SSB_API void* ssb_ipc_open_handle(const unsigned char handle[64])
+{
+	return guarded([&]() -> void* {
+		g_engine.init();
+		cudaIpcMemHandle_t h;
+		memcpy(&h, handle, 64);
+		void* p = nullptr;
+		SSB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		return p;
+	}, nullptr);
+}
+SSB_API int ssb_ipc_close_handle(void* d_ptr) { return d_ptr && cudaIpcCloseMemHandle(d_ptr) == cudaSuccess ? 0 : -1; }
+SSB_API int ssb_export_records_p2p(ssb_index* ix, uint32_t nq, uint32_t limit, void* const* peerRecv, uint32_t nRanks, uint32_t myRank)
+{
+	if (!ix) return -1;
+	return guarded([&] {
+		g_engine.init();
+		std::lock_guard<std::mutex> lk(ix->mu);
+		export_records_p2p(ix->dix, ix->ws, nq, limit, reinterpret_cast<MergeRecord* const*>(peerRecv), nRanks, myRank, ix->stream);
+		SSB_CUDA(cudaStreamSynchronize(ix->stream));      // the peer stores have landed when this returns
+		return 0;
+	}, -1);
+}
+SSB_API int ssb_merge_records_p2p(const void* d_recv, uint32_t nShards, uint32_t nqLocal, uint32_t limit, void* const* peerMerged,
+                                  void* const* peerCounts, uint32_t nRanks, uint32_t myRank)
+{
+	return guarded([&] {
+		g_engine.init();
+		merge_records_p2p(static_cast<const MergeRecord*>(d_recv), nShards, nqLocal, limit, reinterpret_cast<MergeRecord* const*>(peerMerged),
+		                  reinterpret_cast<uint32_t* const*>(peerCounts), nRanks, myRank, 0);
+		SSB_CUDA(cudaStreamSynchronize(0));
+		return 0;
+	}, -1);
+}
+
 }   // extern "C"

@@ -66,12 +66,14 @@ struct DeviceIndex {
 	DevBuf<float> keyEdgeW;      // [E]
 	DevBuf<float> keyWmax;       // [K] wildcard score (max edge weight), -inf when the key has no edge
 	DevBuf<uint64_t> keyRow;     // [K] global first row of the key
+	DevBuf<uint64_t> keyHash;    // [K] 64-bit hash of the key string (shard-independent; multi-GPU merge identity)
 
 	size_t device_bytes() const
 	{
 		return symTable.bytes() + validLut.bytes() + gramCodes.bytes() + gramOff.bytes() + postings.bytes() + termOff.bytes() +
 		       termChars.bytes() + termEdgeOff.bytes() + edgeKid.bytes() + edgeW.bytes() + shortTerms.bytes() + keyOff.bytes() +
-		       keyChars.bytes() + keyEdgeOff.bytes() + keyEdgeTerm.bytes() + keyEdgeW.bytes() + keyWmax.bytes() + keyRow.bytes();
+		       keyChars.bytes() + keyEdgeOff.bytes() + keyEdgeTerm.bytes() + keyEdgeW.bytes() + keyWmax.bytes() + keyRow.bytes() +
+		       keyHash.bytes();
 	}
 };
 

@@ -1,8 +1,11 @@
 // merge.cu — multi-GPU top-k merge (no reference equivalent).
 // Every key-range shard answers the whole query batch and exports, per query, `limit` fixed-size records
-// (score, key length, global first row, key hash). After one all-gather (NCCL, done by the caller) each rank
-// merges: equal key strings from different shards collapse to their best score (the reference's per-key max,
-// nGramSearch.hpp:326), then the global order (score desc, key length asc, first row asc) is cut at `limit`.
+// (score, key length, global first row, key hash), already in rank order. The records travel either through an NCCL
+// collective issued by the caller or — fused — straight from the export kernel into the peers' receive buffers over
+// NVLink (peer-mapped memory). Each rank then merges a slice of the queries: the per-shard runs are merged with the
+// tail of a bitonic network (they are sorted already), equal key strings seen by several shards collapse to their best
+// entry (the reference's per-key max, nGramSearch.hpp:326), and the global order (score desc, key length asc, first
+// row asc) is cut at `limit`.
 #include "search.h"
 #include "textops.cuh"
 #include <algorithm>
@@ -10,46 +13,91 @@
 namespace ssb {
 namespace {
 
+__device__ __forceinline__ MergeRecord make_record(uint32_t q, uint32_t r, const uint32_t* __restrict__ outCount,
+                                                   const uint32_t* __restrict__ outKid, const float* __restrict__ outScore, uint32_t stride,
+                                                   const uint32_t* __restrict__ keyOff, const uint64_t* __restrict__ keyRow,
+                                                   const uint64_t* __restrict__ keyHash)
+{
+	MergeRecord rec;
+	if (r < outCount[q] && r < stride) {
+		const uint32_t kid = outKid[(size_t)q * stride + r];
+		rec.scoreBits = __float_as_uint(outScore[(size_t)q * stride + r]);
+		rec.keyLen = keyOff[kid + 1] - keyOff[kid] - 1;
+		rec.row = keyRow[kid];
+		rec.hash = keyHash[kid];
+	} else {
+		rec.scoreBits = 0; rec.keyLen = 0; rec.row = ~0ull; rec.hash = ~0ull;
+	}
+	return rec;
+}
+
 __global__ void k_export_records(const uint32_t* __restrict__ outCount, const uint32_t* __restrict__ outKid, const float* __restrict__ outScore,
-                                 uint32_t stride, uint32_t nq, uint32_t limit, int unit, const uint32_t* __restrict__ keyOff,
-                                 const uint8_t* __restrict__ keyChars, const uint64_t* __restrict__ keyRow, MergeRecord* __restrict__ out)
+                                 uint32_t stride, uint32_t nq, uint32_t limit, const uint32_t* __restrict__ keyOff,
+                                 const uint64_t* __restrict__ keyRow, const uint64_t* __restrict__ keyHash, MergeRecord* __restrict__ out)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= (uint64_t)nq * limit) return;
 	const uint32_t q = (uint32_t)(i / limit), r = (uint32_t)(i % limit);
-	MergeRecord rec;
-	if (r < outCount[q] && r < stride) {
-		const uint32_t kid = outKid[(size_t)q * stride + r];
-		const uint32_t b = keyOff[kid], len = keyOff[kid + 1] - b - 1;
-		uint64_t h = 0x6b657973ull;
-		if (unit == 1) for (uint32_t j = 0; j < len; ++j) h = hash_step(h, keyChars[b + j]);
-		else for (uint32_t j = 0; j < len; ++j) h = hash_step(h, reinterpret_cast<const uint32_t*>(keyChars)[b + j]);
-		rec.scoreBits = __float_as_uint(outScore[(size_t)q * stride + r]);
-		rec.keyLen = len;
-		rec.row = keyRow[kid];
-		rec.hash = hash_done(h, len);
-	} else {
-		rec.scoreBits = 0; rec.keyLen = 0; rec.row = ~0ull; rec.hash = ~0ull;
-	}
-	out[i] = rec;
+	out[i] = make_record(q, r, outCount, outKid, outScore, stride, keyOff, keyRow, keyHash);
 }
 
-template <bool BY_HASH>
-__device__ __forceinline__ bool rec_less(uint64_t a1, uint64_t b1, uint64_t h1, uint64_t a2, uint64_t b2, uint64_t h2)
+struct PeerPtrs { MergeRecord* p[16]; };
+struct PeerCounts { uint32_t* p[16]; };
+
+// fused export + exchange: the record of query q goes straight into the receive buffer of the rank that merges q
+// (peer-mapped memory, plain 8-byte stores over NVLink): recv[j] is laid out [shard][nq/N][limit].
+__global__ void k_export_records_p2p(const uint32_t* __restrict__ outCount, const uint32_t* __restrict__ outKid,
+                                     const float* __restrict__ outScore, uint32_t stride, uint32_t nq, uint32_t limit,
+                                     const uint32_t* __restrict__ keyOff, const uint64_t* __restrict__ keyRow,
+                                     const uint64_t* __restrict__ keyHash, PeerPtrs peers, uint32_t nRanks, uint32_t myRank)
 {
-	if (BY_HASH && h1 != h2) return h1 < h2;
-	if (a1 != a2) return a1 < a2;
-	return b1 < b2;
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (uint64_t)nq * limit) return;
+	const uint32_t q = (uint32_t)(i / limit), r = (uint32_t)(i % limit);
+	const uint32_t part = nq / nRanks, j = q / part, ql = q - j * part;
+	peers.p[j][((size_t)myRank * part + ql) * limit + r] = make_record(q, r, outCount, outKid, outScore, stride, keyOff, keyRow, keyHash);
 }
-template <bool BY_HASH>
-__device__ void bitonic3(uint64_t* A, uint64_t* B, uint64_t* H, uint32_t p)
+
+__device__ __forceinline__ bool rec_less(uint64_t a1, uint64_t b1, uint64_t a2, uint64_t b2) { return a1 != a2 ? a1 < a2 : b1 < b2; }
+
+// one CTA per query. Shared memory: A (order key hi: ~score | length), B (row), H (hash) of p slots, hash table of 2p u32.
+__global__ void k_merge_records(const MergeRecord* __restrict__ gathered, uint32_t nShards, uint32_t nq, uint32_t limit, uint32_t runLen,
+                                uint32_t p, MergeRecord* __restrict__ merged, uint32_t* __restrict__ counts, PeerPtrs outPeers,
+                                uint32_t nOutPeers, uint32_t outQueryBase, PeerCounts outCountsPeers)
 {
-	for (uint32_t size = 2; size <= p; size <<= 1)
+	extern __shared__ __align__(16) unsigned char mg_smem[];
+	uint64_t* A = reinterpret_cast<uint64_t*>(mg_smem);
+	uint64_t* B = A + p;
+	uint64_t* H = B + p;
+	uint32_t* table = reinterpret_cast<uint32_t*>(H + p);       // 2p slots, 0xFFFFFFFF = empty
+	uint8_t* dead = reinterpret_cast<uint8_t*>(table + 2 * p);   // p flags
+	__shared__ uint32_t sAlive;
+	const uint32_t q = blockIdx.x;
+	// ---- load: run s occupies slots [s*runLen, (s+1)*runLen), ascending for even s, descending for odd s (bitonic layout)
+	for (uint32_t i = threadIdx.x; i < p; i += blockDim.x) {
+		const uint32_t sh = i / runLen, x = i % runLen;
+		const uint32_t r = (sh & 1) ? runLen - 1 - x : x;
+		uint64_t a = ~0ull, b = ~0ull, h = ~0ull;
+		if (sh < nShards && r < limit) {
+			const MergeRecord rec = gathered[((size_t)sh * nq + q) * limit + r];
+			if (rec.row != ~0ull) {
+				a = ((uint64_t)(~float_to_ordered(__uint_as_float(rec.scoreBits))) << 32) | rec.keyLen;
+				b = rec.row; h = rec.hash;
+			}
+		}
+		A[i] = a; B[i] = b; H[i] = h;
+		dead[i] = 0;
+	}
+	for (uint32_t i = threadIdx.x; i < 2 * p; i += blockDim.x) table[i] = 0xFFFFFFFFu;
+	if (threadIdx.x == 0) sAlive = 0;
+	__syncthreads();
+	// ---- the runs are sorted: only the merge stages of the bitonic network remain
+	for (uint32_t size = 2 * runLen; size <= p; size <<= 1)
 		for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
 			for (uint32_t i = threadIdx.x; i < (p >> 1); i += blockDim.x) {
-				uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
-				bool up = (lo & size) == 0;
-				bool lt = rec_less<BY_HASH>(A[hi], B[hi], H[hi], A[lo], B[lo], H[lo]);   // hi < lo
+				const uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+				const bool up = (lo & size) == 0;
+				const bool lt = rec_less(A[hi], B[hi], A[lo], B[lo]);
 				if (lt == up) {
 					uint64_t t;
 					t = A[lo]; A[lo] = A[hi]; A[hi] = t;
@@ -59,56 +107,86 @@ __device__ void bitonic3(uint64_t* A, uint64_t* B, uint64_t* H, uint32_t p)
 			}
 			__syncthreads();
 		}
-}
-
-// one CTA per query
-__global__ void k_merge_records(const MergeRecord* __restrict__ gathered, uint32_t nShards, uint32_t nq, uint32_t limit, uint32_t p,
-                                MergeRecord* __restrict__ merged, uint32_t* __restrict__ counts)
-{
-	extern __shared__ __align__(16) unsigned char mg_smem[];
-	uint64_t* A = reinterpret_cast<uint64_t*>(mg_smem);
-	uint64_t* B = A + p;
-	uint64_t* H = B + p;
-	__shared__ uint32_t sCount;
-	const uint32_t q = blockIdx.x;
-	const uint32_t n = nShards * limit;
+	// ---- equal (hash, length) = the same key string seen by several shards: keep the best-ranked entry
 	for (uint32_t i = threadIdx.x; i < p; i += blockDim.x) {
-		uint64_t a = ~0ull, b = ~0ull, h = ~0ull;
-		if (i < n) {
-			const uint32_t sh = i / limit, r = i % limit;
-			const MergeRecord rec = gathered[((size_t)sh * nq + q) * limit + r];
-			if (rec.row != ~0ull) {
-				a = ((uint64_t)(~float_to_ordered(__uint_as_float(rec.scoreBits))) << 32) | rec.keyLen;
-				b = rec.row; h = rec.hash;
+		if (A[i] == ~0ull) continue;
+		const uint64_t h = H[i];
+		const uint32_t len = (uint32_t)A[i];
+		uint32_t slot = (uint32_t)(mix64(h) & (2 * p - 1));
+		while (true) {
+			const uint32_t cur = atomicCAS(&table[slot], 0xFFFFFFFFu, i);
+			if (cur == 0xFFFFFFFFu) break;                                   // inserted
+			if (H[cur] == h && (uint32_t)A[cur] == len) {
+				const uint32_t prev = atomicMin(&table[slot], i);
+				dead[max(prev, i)] = 1;                                       // the worse-ranked duplicate dies
+				break;
 			}
+			slot = (slot + 1) & (2 * p - 1);
 		}
-		A[i] = a; B[i] = b; H[i] = h;
 	}
-	if (threadIdx.x == 0) sCount = 0;
 	__syncthreads();
-	bitonic3<true>(A, B, H, p);
-	// equal (hash, length) = same key string seen by several shards: keep the best (first) one
-	for (uint32_t base = 0; base < p; base += blockDim.x) {
-		uint32_t i = base + threadIdx.x;
-		bool dead = false;
-		if (i > 0 && i < p) dead = H[i] == H[i - 1] && (uint32_t)A[i] == (uint32_t)A[i - 1] && A[i] != ~0ull;
+	// ---- compact the survivors in rank order (block-wide scan in chunks of blockDim) and cut at `limit`
+	uint32_t base = 0;
+	for (uint32_t c0 = 0; c0 < p && base < limit; c0 += blockDim.x) {
+		const uint32_t i = c0 + threadIdx.x;
+		const bool alive = i < p && A[i] != ~0ull && !dead[i];
+		// warp + block exclusive scan of `alive`
+		const unsigned bal = __ballot_sync(0xffffffffu, alive);
+		__shared__ uint32_t warpSum[32];
+		const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		if (lane == 0) warpSum[warp] = __popc(bal);
 		__syncthreads();
-		if (dead) { A[i] = ~0ull; B[i] = ~0ull; }
-		__syncthreads();
-	}
-	bitonic3<false>(A, B, H, p);
-	for (uint32_t i = threadIdx.x; i < limit; i += blockDim.x) {
-		MergeRecord rec;
-		if (i < p && A[i] != ~0ull) {
+		uint32_t off = 0, tot = 0;
+		for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) { if (w < warp) off += warpSum[w]; tot += warpSum[w]; }
+		const uint32_t pos = base + off + __popc(bal & ((1u << lane) - 1));
+		if (alive && pos < limit) {
+			MergeRecord rec;
 			rec.scoreBits = __float_as_uint(ordered_to_float(~(uint32_t)(A[i] >> 32)));
 			rec.keyLen = (uint32_t)A[i];
 			rec.row = B[i]; rec.hash = H[i];
-			atomicAdd(&sCount, 1u);
-		} else { rec.scoreBits = 0; rec.keyLen = 0; rec.row = ~0ull; rec.hash = ~0ull; }
-		merged[(size_t)q * limit + i] = rec;
+			if (nOutPeers) {
+				for (uint32_t d = 0; d < nOutPeers; ++d) outPeers.p[d][((size_t)(outQueryBase + q)) * limit + pos] = rec;
+			} else merged[(size_t)q * limit + pos] = rec;
+		}
+		base += tot;
+		__syncthreads();
 	}
-	__syncthreads();
-	if (threadIdx.x == 0) counts[q] = sCount;
+	const uint32_t n = min(base, limit);
+	for (uint32_t i = n + threadIdx.x; i < limit; i += blockDim.x) {
+		MergeRecord rec;
+		rec.scoreBits = 0; rec.keyLen = 0; rec.row = ~0ull; rec.hash = ~0ull;
+		if (nOutPeers) {
+			for (uint32_t d = 0; d < nOutPeers; ++d) outPeers.p[d][((size_t)(outQueryBase + q)) * limit + i] = rec;
+		} else merged[(size_t)q * limit + i] = rec;
+	}
+	if (threadIdx.x == 0) {
+		if (nOutPeers) { for (uint32_t d = 0; d < nOutPeers; ++d) outCountsPeers.p[d][outQueryBase + q] = n; }
+		else counts[q] = n;
+	}
+	(void)sAlive;
+}
+
+struct MergeGeom { uint32_t runLen, p; size_t smem; unsigned threads; };
+MergeGeom merge_geometry(uint32_t nShards, uint32_t limit)
+{
+	MergeGeom g;
+	g.runLen = 1;
+	while (g.runLen < limit) g.runLen <<= 1;
+	uint32_t runs = 1;
+	while (runs < nShards) runs <<= 1;
+	g.p = std::max<uint32_t>(2, g.runLen * runs);
+	g.smem = (size_t)g.p * (24 + 8 + 1) + 16;
+	g.threads = std::min<uint32_t>(1024, std::max<uint32_t>(64, g.p / 2));
+	return g;
+}
+void set_merge_smem(size_t smem)
+{
+	static size_t attr = 0;
+	if (smem > 220 * 1024) throw std::runtime_error("merge_records: limit too large for one CTA");
+	if (smem > attr) {
+		SSB_CUDA(cudaFuncSetAttribute(k_merge_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr = smem;
+	}
 }
 
 }   // namespace
@@ -119,31 +197,77 @@ void export_records(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, uin
 	if (nq > ws.capQ) throw std::runtime_error("export_records: no such batch");
 	const uint64_t n = (uint64_t)nq * limit;
 	if (!ix.indexed || ix.K == 0) {
-		// an empty shard contributes only empty slots
-		SSB_CUDA(cudaMemsetAsync(d_out, 0xFF, n * sizeof(MergeRecord), s));
+		SSB_CUDA(cudaMemsetAsync(d_out, 0xFF, n * sizeof(MergeRecord), s));     // an empty shard contributes only empty slots
 		return;
 	}
 	k_export_records<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.outCount.get(), ws.outKid.get(), ws.outScore.get(), limit, nq, limit,
-	                                                             ix.unit, ix.keyOff.get(), ix.keyChars.get(), ix.keyRow.get(), d_out);
+	                                                             ix.keyOff.get(), ix.keyRow.get(), ix.keyHash.get(), d_out);
+	SSB_LAUNCH_CHECK();
+}
+
+void export_records_p2p(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, uint32_t limit, MergeRecord* const* peerRecv,
+                        uint32_t nRanks, uint32_t myRank, cudaStream_t s)
+{
+	if (limit == 0 || limit > FAST_KLIM) throw std::runtime_error("export_records_p2p: limit must be in [1, FAST_KLIM]");
+	if (nq > ws.capQ || nRanks == 0 || nRanks > 16 || nq % nRanks) throw std::runtime_error("export_records_p2p: bad geometry");
+	if (!ix.indexed || ix.K == 0) throw std::runtime_error("export_records_p2p: empty shard");
+	PeerPtrs pp{};
+	for (uint32_t i = 0; i < nRanks; ++i) pp.p[i] = peerRecv[i];
+	const uint64_t n = (uint64_t)nq * limit;
+	k_export_records_p2p<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.outCount.get(), ws.outKid.get(), ws.outScore.get(), limit, nq, limit,
+	                                                                 ix.keyOff.get(), ix.keyRow.get(), ix.keyHash.get(), pp, nRanks, myRank);
+	SSB_LAUNCH_CHECK();
+}
+
+// merges nShards runs per query; when nShards * pow2(limit) exceeds one CTA's shared memory the shards are merged in
+// groups first (top-limit of a union is contained in the union of the groups' top-limits; best-entry dedupe is associative)
+constexpr uint32_t MERGE_MAX_SLOTS = 4096;
+static void merge_impl(const MergeRecord* d_gathered, uint32_t nShards, uint32_t nq, uint32_t limit, MergeRecord* d_out, uint32_t* d_outCount,
+                       const PeerPtrs* peers, const PeerCounts* peerCounts, uint32_t nRanks, uint32_t myRank, cudaStream_t s)
+{
+	MergeGeom g = merge_geometry(nShards, limit);
+	DevBuf<MergeRecord> tmp;
+	DevBuf<uint32_t> tmpCount;
+	while (g.p > MERGE_MAX_SLOTS && nShards > 2) {
+		const uint32_t group = std::max<uint32_t>(2, MERGE_MAX_SLOTS / g.runLen);
+		const uint32_t nGroups = (nShards + group - 1) / group;
+		DevBuf<MergeRecord> next((size_t)nGroups * nq * limit, s);
+		tmpCount.reserve(nq, s);
+		const MergeGeom gg = merge_geometry(group, limit);
+		set_merge_smem(gg.smem);
+		for (uint32_t gi = 0; gi < nGroups; ++gi) {
+			const uint32_t first = gi * group, cnt = std::min(group, nShards - first);
+			PeerPtrs none{}; PeerCounts nonec{};
+			k_merge_records<<<nq, gg.threads, gg.smem, s>>>(d_gathered + (size_t)first * nq * limit, cnt, nq, limit, gg.runLen, gg.p,
+			                                              next.get() + (size_t)gi * nq * limit, tmpCount.get(), none, 0, 0, nonec);
+			SSB_LAUNCH_CHECK();
+		}
+		tmp = std::move(next);
+		d_gathered = tmp.get();
+		nShards = nGroups;
+		g = merge_geometry(nShards, limit);
+	}
+	set_merge_smem(g.smem);
+	PeerPtrs pp{}; PeerCounts pc{};
+	if (peers) { pp = *peers; pc = *peerCounts; }
+	k_merge_records<<<nq, g.threads, g.smem, s>>>(d_gathered, nShards, nq, limit, g.runLen, g.p, d_out, d_outCount, pp, peers ? nRanks : 0,
+	                                              peers ? myRank * nq : 0, pc);
 	SSB_LAUNCH_CHECK();
 }
 
 void merge_records(const MergeRecord* d_gathered, uint32_t nShards, uint32_t nq, uint32_t limit, MergeRecord* d_out, uint32_t* d_outCount,
                    cudaStream_t s)
 {
-	const uint32_t n = nShards * limit;
-	uint32_t p = 2;
-	while (p < n) p <<= 1;
-	const size_t smem = (size_t)p * 24;
-	if (smem > 200 * 1024) throw std::runtime_error("merge_records: nShards * limit too large for one CTA (max 8192 records)");
-	static size_t attr = 0;
-	if (smem > attr) {
-		SSB_CUDA(cudaFuncSetAttribute(k_merge_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		attr = smem;
-	}
-	const unsigned threads = std::min<uint32_t>(1024, std::max<uint32_t>(32, p / 2));
-	k_merge_records<<<nq, threads, smem, s>>>(d_gathered, nShards, nq, limit, p, d_out, d_outCount);
-	SSB_LAUNCH_CHECK();
+	merge_impl(d_gathered, nShards, nq, limit, d_out, d_outCount, nullptr, nullptr, 0, 0, s);
+}
+
+void merge_records_p2p(const MergeRecord* d_recv, uint32_t nShards, uint32_t nqLocal, uint32_t limit, MergeRecord* const* peerMerged,
+                       uint32_t* const* peerCounts, uint32_t nRanks, uint32_t myRank, cudaStream_t s)
+{
+	if (nRanks == 0 || nRanks > 16) throw std::runtime_error("merge_records_p2p: bad geometry");
+	PeerPtrs pp{}; PeerCounts pc{};
+	for (uint32_t i = 0; i < nRanks; ++i) { pp.p[i] = peerMerged[i]; pc.p[i] = peerCounts[i]; }
+	merge_impl(d_recv, nShards, nqLocal, limit, nullptr, nullptr, &pp, &pc, nRanks, myRank, s);
 }
 
 }   // namespace ssb

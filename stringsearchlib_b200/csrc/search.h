@@ -101,5 +101,11 @@ struct MergeRecord {
 void export_records(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, uint32_t limit, MergeRecord* d_out, cudaStream_t s);
 void merge_records(const MergeRecord* d_gathered, uint32_t nShards, uint32_t nq, uint32_t limit, MergeRecord* d_out, uint32_t* d_outCount,
                    cudaStream_t s);
+// fused variants over peer-mapped memory (NVLink P2P stores): export writes query q's records into the receive buffer of
+// the rank that merges q ([shard][nq/N][limit]); merge writes its slice of final records/counts into every rank's buffers.
+void export_records_p2p(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, uint32_t limit, MergeRecord* const* peerRecv,
+                        uint32_t nRanks, uint32_t myRank, cudaStream_t s);
+void merge_records_p2p(const MergeRecord* d_recv, uint32_t nShards, uint32_t nqLocal, uint32_t limit, MergeRecord* const* peerMerged,
+                       uint32_t* const* peerCounts, uint32_t nRanks, uint32_t myRank, cudaStream_t s);
 
 }   // namespace ssb

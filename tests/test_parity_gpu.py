@@ -308,6 +308,86 @@ def test_key_range_shards_merge(ssb, oracle_built):
             ix.close()
 
 
+def test_key_range_shards_p2p_exchange(ssb, oracle_built):
+    """the fused exchange (export kernel stores into the merging rank's buffer, merge kernel stores into every rank's result
+    buffer) with N emulated ranks on one GPU: all buffers are local, the indexing is the multi-GPU one."""
+    from stringsearchlib_b200 import synth
+    from stringsearchlib_b200 import api
+    n, nq, limit, N = 40000, 128, 20, 4
+    keys = synth.ascii_keys(n)
+    q = synth.queries_from(keys, nq)
+    S = oracle_built.SpecIndex(keys, 1)
+    o = S.tables()
+    counts, ext, sc = S.search_batch(q, 0.0, limit)
+    rb = api.RECORD_DTYPE.itemsize
+    part = nq // N
+    recv = [api.device_alloc(N * part * limit * rb) for _ in range(N)]
+    merged = [api.device_alloc(nq * limit * rb) for _ in range(N)]
+    cnts = [api.device_alloc(nq * 4) for _ in range(N)]
+    bounds = np.linspace(0, n, N + 1).astype(int)
+    shards = []
+    for r in range(N):
+        ix = ssb.Index(keys.slice(bounds[r], bounds[r + 1]), 1, row_base=int(bounds[r]))
+        ix.search_batch(q, 0.0, limit)
+        ix.export_records_p2p(nq, limit, recv, r)
+        shards.append(ix)
+    for r in range(N):
+        api.merge_records_p2p(recv[r], N, part, limit, merged, cnts, r)
+    for r in range(N):
+        rec = np.zeros((nq, limit), api.RECORD_DTYPE)
+        mc = np.zeros(nq, np.uint32)
+        api.memcpy_d2h(rec, merged[r])
+        api.memcpy_d2h(mc, cnts[r])
+        assert np.array_equal(mc, counts)
+        for i in range(nq):
+            c = int(counts[i])
+            assert np.array_equal(rec["scoreBits"][i, :c], sc[i, :c].view(np.uint32))
+            assert np.array_equal(rec["row"][i, :c], o["firstRowExt"][ext[i, :c]])
+    for ix in shards:
+        ix.close()
+    for p in recv + merged + cnts:
+        api.device_free(p)
+
+
+def test_merge_collapses_duplicates_and_large_limit(ssb, oracle_built):
+    """the same key strings in several shards collapse to one entry (best score); 8 shards x limit 1000 exercises the
+    hierarchical merge (more records than one CTA's shared memory holds)."""
+    import torch
+    from stringsearchlib_b200 import synth
+    from stringsearchlib_b200.api import RECORD_DTYPE, merge_records
+    n, nq, limit, shards = 24000, 32, 1000, 8
+    keys = synth.ascii_keys(n)
+    words = [keys.get(i) for i in range(n)]
+    # every shard also holds a copy of the first 50 keys: duplicates across shards
+    per = n // shards
+    q = synth.queries_from(keys, nq)
+    S = oracle_built.SpecIndex(words, 1)
+    o = S.tables()
+    counts, ext, sc = S.search_batch(q, 0.0, limit)
+    gathered = torch.empty((shards, nq, limit, RECORD_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    idx = []
+    for s in range(shards):
+        mine = words[s * per:(s + 1) * per] + (words[:50] if s else [])
+        ix = ssb.Index(mine, 1, row_base=s * per if s == 0 else s * per)
+        # rows of the duplicated tail sit after the shard's own rows, so their global row ids are larger than the originals'
+        ix.search_batch(q, 0.0, limit)
+        ix.export_records(nq, limit, gathered[s].data_ptr())
+        idx.append(ix)
+    merged = torch.empty((nq, limit, RECORD_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    mcount = torch.empty(nq, dtype=torch.int32, device="cuda")
+    merge_records(gathered.data_ptr(), shards, nq, limit, merged.data_ptr(), mcount.data_ptr())
+    torch.cuda.synchronize()
+    rec = merged.cpu().numpy().view(RECORD_DTYPE).reshape(nq, limit)
+    mc = mcount.cpu().numpy()
+    assert np.array_equal(mc, counts)
+    for i in range(nq):
+        c = int(counts[i])
+        assert np.array_equal(rec["scoreBits"][i, :c], sc[i, :c].view(np.uint32))
+        assert np.array_equal(rec["keyLen"][i, :c], np.diff(o["keyOffExt"]).astype(np.uint32)[ext[i, :c]])
+    for ix in idx:
+        ix.close()
+
+
 def test_properties_full_size(ssb):
     """size-independent properties at 1M keys (the oracle is not run): sorted scores, deterministic repeat,
     unmodified key ranks first, resident rerun identical, no dense fallback on this distribution."""
