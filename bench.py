@@ -265,9 +265,10 @@ def main():
               act as cross-rank barriers.
         nccl: all-to-all of the records, merge kernel, all-gather of the merged slices."""
         if use_p2p:
+            # everything below is enqueued on the default stream: kernel -> 4-byte all-reduce (cross-rank barrier: all
+            # exports have landed) -> kernel -> all-reduce (all merged slices have landed); one host sync at the end
             ix.export_records_p2p(args.batch, args.limit, peer_recv, rank)
             dist.all_reduce(flag)
-            torch.cuda.synchronize()
             api.merge_records_p2p(recv_ptr, world, part_q, args.limit, peer_merged, peer_counts, rank)
             dist.all_reduce(flag)
             torch.cuda.synchronize()
@@ -281,6 +282,7 @@ def main():
         else:
             dist.all_gather_into_tensor(gathered, mine)
             merge_records(gathered.data_ptr(), world, args.batch, args.limit, merged.data_ptr(), mcount.data_ptr())
+        torch.cuda.synchronize()
 
     def results_to_host():
         if use_p2p:

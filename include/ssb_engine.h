@@ -66,8 +66,9 @@ int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uint32_t li
 /* ---- multi-GPU (key-range shards, one process per GPU): fixed-size per-query records for an all-gather ----
  * record = { u32 scoreBits, u32 keyLen, u64 row, u64 keyHash } (24 bytes); a query's unused slots have row = ~0.
  * d_out / d_gathered / d_merged are DEVICE pointers: [nq][limit] per shard, shards concatenated on gather.
- * ssb_export_records returns after its kernel has finished; ssb_merge_records only ENQUEUES on the legacy default
- * stream (so it is ordered behind collectives enqueued there) — synchronise before reading d_merged on the host. */
+ * All four export/merge calls only ENQUEUE their kernels on the legacy default stream, so they are ordered with the
+ * collectives the caller enqueues there (torch's default stream) without host round trips — synchronise before reading
+ * results on the host. The batch they export must be complete (ssb_search_* calls return synchronised). */
 int ssb_export_records(ssb_index* ix, uint32_t nq, uint32_t limit, void* d_out);
 int ssb_merge_records(const void* d_gathered, uint32_t nShards, uint32_t nq, uint32_t limit, void* d_merged, uint32_t* d_counts);
 

@@ -485,8 +485,9 @@ SSB_API int ssb_export_records(ssb_index* ix, uint32_t nq, uint32_t limit, void*
 	return guarded([&] {
 		g_engine.init();
 		std::lock_guard<std::mutex> lk(ix->mu);
-		export_records(ix->dix, ix->ws, nq, limit, static_cast<MergeRecord*>(d_out), ix->stream);
-		SSB_CUDA(cudaStreamSynchronize(ix->stream));
+		// the batch's results are complete (search calls synchronise their stream); everything of the exchange is only
+		// ENQUEUED on the legacy default stream, in order with the caller's collectives
+		export_records(ix->dix, ix->ws, nq, limit, static_cast<MergeRecord*>(d_out), 0);
 		return 0;
 	}, -1);
 }
@@ -544,8 +545,7 @@ SSB_API int ssb_export_records_p2p(ssb_index* ix, uint32_t nq, uint32_t limit, v
 	return guarded([&] {
 		g_engine.init();
 		std::lock_guard<std::mutex> lk(ix->mu);
-		export_records_p2p(ix->dix, ix->ws, nq, limit, reinterpret_cast<MergeRecord* const*>(peerRecv), nRanks, myRank, ix->stream);
-		SSB_CUDA(cudaStreamSynchronize(ix->stream));      // the peer stores have landed when this returns
+		export_records_p2p(ix->dix, ix->ws, nq, limit, reinterpret_cast<MergeRecord* const*>(peerRecv), nRanks, myRank, 0);
 		return 0;
 	}, -1);
 }
@@ -556,7 +556,6 @@ SSB_API int ssb_merge_records_p2p(const void* d_recv, uint32_t nShards, uint32_t
 		g_engine.init();
 		merge_records_p2p(static_cast<const MergeRecord*>(d_recv), nShards, nqLocal, limit, reinterpret_cast<MergeRecord* const*>(peerMerged),
 		                  reinterpret_cast<uint32_t* const*>(peerCounts), nRanks, myRank, 0);
-		SSB_CUDA(cudaStreamSynchronize(0));
 		return 0;
 	}, -1);
 }

@@ -293,6 +293,7 @@ def test_key_range_shards_merge(ssb, oracle_built):
             ix.search_batch(q, 0.0, limit)
             ix.export_records(nq, limit, gathered[s].data_ptr())
             idx.append(ix)
+        torch.cuda.synchronize()
         merged = torch.empty((nq, limit, RECORD_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
         mcount = torch.empty(nq, dtype=torch.int32, device="cuda")
         merge_records(gathered.data_ptr(), shards, nq, limit, merged.data_ptr(), mcount.data_ptr())
@@ -333,6 +334,8 @@ def test_key_range_shards_p2p_exchange(ssb, oracle_built):
         shards.append(ix)
     for r in range(N):
         api.merge_records_p2p(recv[r], N, part, limit, merged, cnts, r)
+    import torch
+    torch.cuda.synchronize()
     for r in range(N):
         rec = np.zeros((nq, limit), api.RECORD_DTYPE)
         mc = np.zeros(nq, np.uint32)
