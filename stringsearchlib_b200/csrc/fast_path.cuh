@@ -47,9 +47,12 @@ struct FastShared {
 	uint32_t exactKey[MAX_QGRAMS + 1]; // ~ordered(value) of a weight-1, unpromoted candidate with count c
 	float sOf[MAX_QGRAMS + 1];         // term score for count c
 	unsigned long long tau;
+	uint32_t promotedKey;              // key high word of an exact match (score 100)
 	uint32_t bufCount, overflow, query, selPrefixLo, selK;
 	uint32_t passLo, passHi, searchTop, cRej, lastPass, prefetched;
 	uint32_t qlen, nGrams, cmin, cprom, allOnes, nLists, total;
+	int topShift, kidBits;             // radix-select digit range (see select_smallest)
+	uint32_t classMode;                // 1: key high word = score-class rank (uniform weights), 0: ~ordered(score)
 	IndexView ix;
 };
 
@@ -99,17 +102,21 @@ __device__ __forceinline__ uint32_t lower_bound_smem(const uint32_t* a, uint32_t
 }
 
 // keeps the k smallest entries of buf[0..n) (all distinct), sets tau to the k-th smallest. CTA-wide.
+// MSD radix select over 8-bit digits; digits known to be zero in every entry are skipped: the high word is a score-class
+// rank < 256 in uniform-weight mode (topShift = 32), and kids have kidBits significant bits.
 __device__ void select_smallest(FastShared& sh, uint32_t n, uint32_t k)
 {
 	const int tid = threadIdx.x;
 	unsigned long long prefix = 0;
 	uint32_t kk = k;
-	for (int shift = 56; shift >= 0; shift -= 8) {
+	const int topShift = sh.topShift, kidBits = sh.kidBits;
+	for (int shift = topShift; shift >= 0; shift -= 8) {
+		if (shift < 32 && shift >= kidBits) { prefix <<= 8; continue; }      // this kid byte is zero everywhere
 		for (int i = tid; i < 256; i += FS_THREADS) sh.hist[i] = 0;
 		__syncthreads();
 		for (uint32_t i = tid; i < n; i += FS_THREADS) {
 			unsigned long long v = sh.buf[i];
-			if (shift == 56 || (v >> (shift + 8)) == prefix) atomicAdd(&sh.hist[(uint32_t)(v >> shift) & 255u], 1u);
+			if (shift == topShift || (v >> (shift + 8)) == prefix) atomicAdd(&sh.hist[(uint32_t)(v >> shift) & 255u], 1u);
 		}
 		__syncthreads();
 		if (tid < 32) {
@@ -176,7 +183,7 @@ __device__ __noinline__ void emit_candidate(FastShared& sh, const U* __restrict_
 	if (ix.identity && ix.uniformW) {
 		const uint32_t kid = m;
 		uint32_t hk = sh.exactKey[c];
-		if (c >= cprom && key_equals_query<U>(ix, kid, qn, qlen)) hk = ~float_to_ordered(100.0f);   // hpp:333-335
+		if (c >= cprom && key_equals_query<U>(ix, kid, qn, qlen)) hk = sh.promotedKey;              // hpp:333-335
 		const unsigned long long key = ((unsigned long long)hk << 32) | kid;
 		if (key < tau) {
 			uint32_t idx = atomicAdd(&sh.bufCount, 1u);
@@ -391,19 +398,34 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 				sh.cur[tid] = 0; sh.rem[tid] = d.listLen[tid]; sh.mult[tid] = d.listMult[tid];
 			} else { sh.rem[tid] = 0; sh.mult[tid] = 0; sh.nTake[tid] = 0; sh.cur[tid] = 0; sh.listOff[tid] = 0; }
 		}
+		// identity + uniform weights: a candidate's value is fully determined by its match count, so the key's high word is the
+		// RANK of the score class (0 = exact match promoted to 100, then nGrams matches, ..., 1 match) instead of the float bits
+		// — same order, 8 significant bits for the radix select. Otherwise: ~ordered(float value).
+		const bool classMode = ix.identity && ix.uniformW;
 		if (tid <= MAX_QGRAMS) {
 			const uint32_t c = tid;
 			float s = (c <= nGrams && nGrams) ? term_score(c, nGrams) : 0.0f;
 			sh.sOf[c] = s;
-			// identity/uniform: the exact value (weight 1); otherwise an upper bound over all edges of any term
-			float ub = ix.uniformW ? edge_value(1.0f, s) : edge_value(ix.wmax, s);
-			sh.exactKey[c] = ~float_to_ordered(edge_value(1.0f, s));
-			if (c >= d.cprom) ub = fmaxf(ub, 100.0f);
-			sh.hiKey[c] = ~float_to_ordered(ub);
+			if (classMode) {
+				sh.exactKey[c] = c <= nGrams ? nGrams - c + 1 : 255u;
+				sh.hiKey[c] = c >= d.cprom ? 0u : sh.exactKey[c];
+			} else {
+				// an upper bound over all edges of any term with this count
+				float ub = ix.uniformW ? edge_value(1.0f, s) : edge_value(ix.wmax, s);
+				sh.exactKey[c] = ~float_to_ordered(edge_value(1.0f, s));
+				if (c >= d.cprom) ub = fmaxf(ub, 100.0f);
+				sh.hiKey[c] = ~float_to_ordered(ub);
+			}
 		}
 		if (tid == 0) {
 			sh.bufCount = 0; sh.overflow = 0; sh.tau = ~0ull; sh.passLo = 0; sh.prefetched = 0;
 			sh.qlen = d.qlen; sh.nGrams = nGrams; sh.cmin = d.cmin; sh.cprom = d.cprom; sh.nLists = nLists; sh.total = d.total;
+			sh.classMode = classMode;
+			sh.promotedKey = classMode ? 0u : ~float_to_ordered(100.0f);
+			sh.topShift = classMode ? 32 : 56;
+			int kb = 1;
+			while (kb < 32 && (1ull << kb) < ix.K) ++kb;
+			sh.kidBits = kb;
 			uint32_t ones = 1;
 			for (uint32_t i = 0; i < nLists; ++i) ones &= d.listMult[i] == 1;
 			sh.allOnes = ones;
@@ -522,7 +544,8 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 		for (uint32_t i = tid; i < level; i += FS_THREADS) {
 			unsigned long long v = sh.buf[i];
 			outKid[(size_t)q * outStride + i] = (uint32_t)v;
-			outScore[(size_t)q * outStride + i] = rank_key_score(v);
+			const uint32_t hi = (uint32_t)(v >> 32);
+			outScore[(size_t)q * outStride + i] = sh.classMode ? (hi == 0 ? 100.0f : edge_value(1.0f, sh.sOf[nGrams - hi + 1])) : rank_key_score(v);
 		}
 		if (tid == 0) {
 			outCount[q] = level;
