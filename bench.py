@@ -307,12 +307,16 @@ def main():
         # (1) end to end through the C ABI with host buffers
         barrier()
         t0 = time.perf_counter()
-        bp = ix.search_batch_raw(qptrs[s], args.batch, args.threshold, args.limit)   # H2D + kernels + D2H inside
-        n_results = int(bp.contents.offsets[args.batch])
-        ix.free_raw(bp)
-        if world > 1:
+        if world == 1:
+            bp = ix.search_batch_raw(qptrs[s], args.batch, args.threshold, args.limit)   # H2D + kernels + D2H inside
+            n_results = int(bp.contents.offsets[args.batch])
+            ix.free_raw(bp)
+        else:
+            # sharded: H2D + kernels on every rank, cross-shard merge, then ONE D2H of the merged records
+            ix.search_batch_device(qptrs[s], args.batch, args.threshold, args.limit)
             exchange()
             results_to_host()
+            n_results = int(host_cnt.sum().item())
         t1 = time.perf_counter()
         # (2) device part only, the same batch resident in HBM
         barrier()

@@ -58,6 +58,10 @@ ssb_batch* ssb_search_batch_packed(ssb_index* ix, const void* units, const uint3
                                    uint32_t limit);
 void ssb_batch_free(ssb_batch* b);
 
+/* uploads and answers a batch but leaves the per-shard results in HBM (multi-GPU: they go through ssb_export_records*
+ * and the cross-shard merge instead of back to this host). 0 on success. */
+int ssb_search_batch_device(ssb_index* ix, const void* const* queries, uint32_t nq, float threshold, uint32_t limit);
+
 /* re-runs the device part of the last uploaded batch (queries resident in HBM, results left in HBM);
  * ms[0] = whole device part, ms[1] = k_fast_search alone (CUDA events on the engine's stream).
  * stats[]: 0 nFast 1 nDense 2 nOverflow 3 postings touched by fast queries */

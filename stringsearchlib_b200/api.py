@@ -58,6 +58,7 @@ def core_library():
     lib.ssb_search_batch_packed.restype = POINTER(_Batch)
     lib.ssb_search_batch_packed.argtypes = [c_void_p, c_void_p, POINTER(c_uint32), c_uint32, c_float, c_uint32]
     lib.ssb_batch_free.argtypes = [POINTER(_Batch)]
+    lib.ssb_search_batch_device.argtypes = [c_void_p, POINTER(c_void_p), c_uint32, c_float, c_uint32]
     lib.ssb_search_resident.argtypes = [c_void_p, c_uint32, c_float, c_uint32, POINTER(c_float), POINTER(c_uint64)]
     lib.ssb_export_records.argtypes = [c_void_p, c_uint32, c_uint32, c_void_p]
     lib.ssb_merge_records.argtypes = [c_void_p, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p]
@@ -274,6 +275,11 @@ class Index:
         if not bp:
             raise RuntimeError("ssb_search_batch failed: " + self._lib.ssb_last_error().decode())
         return bp
+
+    def search_batch_device(self, ptrs, nq, threshold=0.0, limit=100):
+        """H2D + kernels; the per-shard results stay in HBM (sharded path: export_records* + cross-shard merge follow)."""
+        if self._lib.ssb_search_batch_device(self._h, ptrs, nq, threshold, limit) != 0:
+            raise RuntimeError(self._lib.ssb_last_error().decode())
 
     def free_raw(self, bp):
         self._lib.ssb_batch_free(bp)

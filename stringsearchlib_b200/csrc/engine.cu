@@ -436,6 +436,38 @@ SSB_API ssb_batch* ssb_search_batch_packed(ssb_index* ix, const void* units, con
 		return run_batch(ix, units, offsets, nq, threshold, limit);
 	}, nullptr);
 }
+// packs NUL-terminated query strings into the index's pinned staging; returns the offsets array
+static const uint32_t* pack_queries(ssb_index* ix, const void* const* queries, uint32_t nq)
+{
+	const int unit = ix->dix.unit;
+	ix->pinQOff.reserve(nq + 1);
+	uint32_t* off = ix->pinQOff.get();
+	uint64_t total = 0;
+	for (uint32_t q = 0; q < nq; ++q) {
+		off[q] = (uint32_t)total;
+		const void* p = queries[q];
+		total += !p ? 0 : (unit == 1 ? strlen((const char*)p) : wcslen((const wchar_t*)p));
+	}
+	off[nq] = (uint32_t)total;
+	ix->pinQ.reserve(std::max<uint64_t>(total * unit, 16));
+	for (uint32_t q = 0; q < nq; ++q)
+		if (queries[q]) memcpy(ix->pinQ.get() + (size_t)off[q] * unit, queries[q], (size_t)(off[q + 1] - off[q]) * unit);
+	return off;
+}
+
+SSB_API int ssb_search_batch_device(ssb_index* ix, const void* const* queries, uint32_t nq, float threshold, uint32_t limit)
+{
+	if (!ix) return -1;
+	return guarded([&] {
+		g_engine.init();
+		std::lock_guard<std::mutex> lk(ix->mu);
+		const uint32_t* off = pack_queries(ix, queries, nq);
+		BatchOutput out;
+		search_batch(ix->dix, ix->ws, ix->pinQ.get(), off, nq, threshold, limit, out, ix->stream, &ix->lastStats, nullptr, true);
+		return 0;
+	}, -1);
+}
+
 SSB_API ssb_batch* ssb_search_batch(ssb_index* ix, const void* const* queries, uint32_t nq, float threshold, uint32_t limit)
 {
 	if (!ix) return nullptr;

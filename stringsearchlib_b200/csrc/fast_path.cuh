@@ -172,6 +172,18 @@ __device__ void sort_buffer(FastShared& sh, uint32_t n)
 		}
 }
 
+// appends one key per calling lane; lanes that arrive together share one shared-memory atomic (opportunistic warp aggregation)
+__device__ __forceinline__ void append_key(FastShared& sh, unsigned long long key)
+{
+	const unsigned am = __activemask();
+	const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
+	uint32_t base = 0;
+	if (lane == leader) base = atomicAdd(&sh.bufCount, (uint32_t)__popc(am));
+	base = __shfl_sync(am, base, leader);
+	const uint32_t idx = base + __popc(am & ((1u << lane) - 1));
+	if (idx < sh.bufCap) sh.buf[idx] = key; else sh.overflow = 1;
+}
+
 // A term reached `c` matches: evaluate its keys (hpp:310-341) and append what can still make the top-k.
 // Called only for terms that survive the integer pre-filter, i.e. rarely once tau is established -> not inlined.
 template <class U>
@@ -185,10 +197,7 @@ __device__ __noinline__ void emit_candidate(FastShared& sh, const U* __restrict_
 		uint32_t hk = sh.exactKey[c];
 		if (c >= cprom && key_equals_query<U>(ix, kid, qn, qlen)) hk = sh.promotedKey;              // hpp:333-335
 		const unsigned long long key = ((unsigned long long)hk << 32) | kid;
-		if (key < tau) {
-			uint32_t idx = atomicAdd(&sh.bufCount, 1u);
-			if (idx < sh.bufCap) sh.buf[idx] = key; else sh.overflow = 1;
-		}
+		if (key < tau) append_key(sh, key);
 		return;
 	}
 	const float s = sh.sOf[c];
@@ -214,8 +223,7 @@ __device__ __noinline__ void emit_candidate(FastShared& sh, const U* __restrict_
 			dominated = v2 > v || (v2 == v && t2 < m);
 		}
 		if (dominated) continue;
-		uint32_t idx = atomicAdd(&sh.bufCount, 1u);
-		if (idx < sh.bufCap) sh.buf[idx] = key; else sh.overflow = 1;
+		append_key(sh, key);
 	}
 }
 

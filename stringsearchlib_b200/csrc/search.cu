@@ -584,7 +584,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 }   // namespace
 
 void search_batch(const DeviceIndex& ix, SearchWorkspace& ws, const void* qchars, const uint32_t* qoff, uint32_t nq, float threshold,
-                  uint32_t limit, BatchOutput& out, cudaStream_t s, SearchStats* stats, HostResult* hr)
+                  uint32_t limit, BatchOutput& out, cudaStream_t s, SearchStats* stats, HostResult* hr, bool deviceOnly)
 {
 	out = BatchOutput();
 	out.nq = nq;
@@ -599,6 +599,7 @@ void search_batch(const DeviceIndex& ix, SearchWorkspace& ws, const void* qchars
 	SSB_CUDA(cudaMemcpyAsync(ws.qoff.get(), qoff, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
 	if (ix.unit == 1) run_device<uint8_t>(ix, ws, nq, threshold, limit, stride, &out, s, stats);
 	else run_device<uint32_t>(ix, ws, nq, threshold, limit, stride, &out, s, stats);
+	if (deviceOnly) return;          // sharded path: results stay in HBM for the cross-shard merge
 	if (hr && out.big.empty() && ix.K && hr->capQ >= nq && hr->capResults >= (size_t)nq * stride) {
 		// device-side CSR compaction + gather of row ids / string addresses, D2H straight into the caller's pinned arrays
 		uint32_t* anyBig = ws.counters.get() + 4;

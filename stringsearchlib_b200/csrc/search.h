@@ -84,7 +84,7 @@ struct BatchOutput {
 // When hr != nullptr and no query overflowed the fixed stride, the device compacts the results to CSR, gathers row ids and
 // string pointers, and copies straight into hr (out.csr = true); otherwise the fixed-stride arrays of `out` are filled.
 void search_batch(const DeviceIndex& ix, SearchWorkspace& ws, const void* qchars, const uint32_t* qoff, uint32_t nq, float threshold,
-                  uint32_t limit, BatchOutput& out, cudaStream_t s, SearchStats* stats, HostResult* hr = nullptr);
+                  uint32_t limit, BatchOutput& out, cudaStream_t s, SearchStats* stats, HostResult* hr = nullptr, bool deviceOnly = false);
 
 // Device-resident variant used for kernel-only timing: queries must already have been uploaded by a previous
 // search_batch() call with the same arguments; re-runs prep + fast/dense kernels, leaves results on the device.
