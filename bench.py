@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--cpu-keys", type=int, default=1_000_000, help="vocabulary prefix indexed by the CPU reference leg")
     ap.add_argument("--cpu-queries", type=int, default=256, help="queries per step of the CPU reference leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-exchange", action="store_true", help="N>1: print CUDA-event times of the exchange phases (stderr)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: fused export/merge kernels storing into NVLink peer memory (default) or NCCL all-to-all + all-gather")
     args = ap.parse_args()
@@ -258,6 +259,16 @@ def main():
         else:
             gathered = torch.empty((world, args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
 
+    xprof = []
+    if world > 1:
+        xev0, xev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def exchange_timed():
+        """exchange() bracketed by CUDA events on the stream it is enqueued on; returns device milliseconds"""
+        xev0.record()
+        exchange()
+        return xev0.elapsed_time(xev1)
+
     def exchange():
         """per-query top-k merge across the key-range shards; every rank merges a 1/N slice of the queries.
         p2p : the export kernel stores each record into the merging rank's buffer over NVLink, the merge kernel stores its
@@ -267,11 +278,20 @@ def main():
         if use_p2p:
             # everything below is enqueued on the default stream: kernel -> 4-byte all-reduce (cross-rank barrier: all
             # exports have landed) -> kernel -> all-reduce (all merged slices have landed); one host sync at the end
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if args.profile_exchange else None
+            if ev: ev[0].record()
             ix.export_records_p2p(args.batch, args.limit, peer_recv, rank)
+            if ev: ev[1].record()
             dist.all_reduce(flag)
+            if ev: ev[2].record()
             api.merge_records_p2p(recv_ptr, world, part_q, args.limit, peer_merged, peer_counts, rank)
+            if ev: ev[3].record()
             dist.all_reduce(flag)
+            if ev: ev[4].record()
+            xev1.record()
             torch.cuda.synchronize()
+            if ev and rank == 0:
+                xprof.append([ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
             return
         ix.export_records(args.batch, args.limit, mine.data_ptr())
         if sliced:
@@ -282,6 +302,7 @@ def main():
         else:
             dist.all_gather_into_tensor(gathered, mine)
             merge_records(gathered.data_ptr(), world, args.batch, args.limit, merged.data_ptr(), mcount.data_ptr())
+        xev1.record()
         torch.cuda.synchronize()
 
     def results_to_host():
@@ -323,7 +344,7 @@ def main():
         t2 = time.perf_counter()
         ms, msk, st = ix.search_resident(args.batch, args.threshold, args.limit)
         if world > 1:
-            exchange()
+            ms += exchange_timed()          # device time of the step = search (engine-stream events) + exchange (default-stream events)
         torch.cuda.synchronize()
         t3 = time.perf_counter()
         if timed:
@@ -356,13 +377,16 @@ def main():
         return t.tolist()
 
     step_s, e2e_s, dev_ms, fast_ms = agg_max(step_s), agg_max(e2e_s), agg_max(dev_ms), agg_max(fast_ms)
+    if xprof and rank == 0:
+        m = np.median(np.array(xprof), axis=0)
+        sys.stderr.write(f"[exchange ms] export={m[0]:.3f} barrier1={m[1]:.3f} merge={m[2]:.3f} barrier2={m[3]:.3f}\n")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # N == 1: the device part is timed by CUDA events on the engine's stream; N > 1: the step spans the engine's stream
-    # and NCCL's, so it is bracketed by barrier + synchronize and wall-clocked (max over ranks)
-    step_ms = float(np.mean(dev_ms)) if world == 1 else 1e3 * float(np.mean(step_s))
+    # device time of a step, CUDA events on the streams the work is enqueued on, max over ranks per step:
+    # search (engine stream) [+ exchange (default stream) for N > 1]; the wall-clocked step is reported beside it
+    step_ms = float(np.mean(dev_ms))
     value = args.batch / (step_ms / 1e3)
     e2e = args.batch / float(np.mean(e2e_s))
     peak, peak_src = read_peaks()
@@ -379,7 +403,7 @@ def main():
         except (OSError, ValueError):
             traffic = None
     line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "ms_per_step": step_ms, "wall_ms_per_step": 1e3 * float(np.mean(step_s)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(np.mean(e2e_s))},
