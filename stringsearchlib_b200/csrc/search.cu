@@ -484,8 +484,8 @@ void ensure_workspace(SearchWorkspace& ws, uint32_t nq, size_t charBytes, uint32
 	if (!ws.ev0) {
 		SSB_CUDA(cudaEventCreate(&ws.ev0)); SSB_CUDA(cudaEventCreate(&ws.ev1));
 		SSB_CUDA(cudaEventCreate(&ws.ev2)); SSB_CUDA(cudaEventCreate(&ws.ev3));
-		ws.counters.alloc(8, s);
-		ws.statCounters.alloc(4, s);
+		ws.counters.alloc(16, s);
+		ws.hostCounters.reserve(16);
 	}
 	if (nq > ws.capQ || stride > ws.stride) {
 		uint32_t cq = std::max(nq, ws.capQ), st = std::max(stride, ws.stride);
@@ -503,7 +503,7 @@ void ensure_workspace(SearchWorkspace& ws, uint32_t nq, size_t charBytes, uint32
 
 template <class U>
 void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float threshold, uint32_t limit, uint32_t stride,
-                BatchOutput* out, cudaStream_t s, SearchStats* st)
+                BatchOutput* out, cudaStream_t s, SearchStats* st, HostResult* hr)
 {
 	const IndexView v = make_view(ix);
 	// candidate buffer: 2 * limit entries rounded up to a power of two (>= 1024); it decides the CTA's shared memory
@@ -521,27 +521,23 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		const int maxSmem = (int)(((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)FS_BUF_MAX * 8);
 		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
 		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+		SSB_CUDA(cudaFuncSetAttribute(k_order_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ORDER_MAX * 8)));
 	}
 	if (!ctasFor[cfg]) {
 		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasFor[cfg], k_fast_search<U>, FS_THREADS, smemBytes));
 		if (ctasFor[cfg] < 1) ctasFor[cfg] = 1;
 	}
 	const int ctasPerSM = ctasFor[cfg];
+	unsigned long long* statCounters = reinterpret_cast<unsigned long long*>(ws.counters.get() + 8);
 	SSB_CUDA(cudaEventRecord(ws.ev0, s));
 	ws.counters.zero(s);
-	ws.statCounters.zero(s);
 	const U* qc = reinterpret_cast<const U*>(ws.qchars.get());
 	U* qn = reinterpret_cast<U*>(ws.qnorm.get());
 	k_query_prep<U><<<grid_for((size_t)nq * 32), 256, 0, s>>>(v, qc, ws.qoff.get(), nq, threshold, limit, qn, ws.desc.get(),
 	                                                          ws.fastList.get(), ws.denseList.get(), ws.counters.get(),
 	                                                          ws.outCount.get());
 	SSB_LAUNCH_CHECK();
-	if (nq <= ORDER_MAX) {
-		static bool orderAttr = false;
-		if (!orderAttr) {
-			SSB_CUDA(cudaFuncSetAttribute(k_order_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ORDER_MAX * 8)));
-			orderAttr = true;
-		}
+	if (nq >= 256 && nq <= ORDER_MAX) {      // a handful of queries gain nothing from LPT order
 		k_order_fast<<<1, 1024, ORDER_MAX * 8, s>>>(ws.desc.get(), ws.fastList.get(), ws.counters.get());
 		SSB_LAUNCH_CHECK();
 	}
@@ -550,13 +546,40 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	const unsigned grid = (unsigned)std::min<size_t>((size_t)numSMs * ctasPerSM, std::max<uint32_t>(nq, 1));
 	k_fast_search<U><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(), ws.denseList.get(),
 	                                                     limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(),
-	                                                     ws.statCounters.get(), bufCap);
+	                                                     statCounters, bufCap);
 	SSB_LAUNCH_CHECK();
 	SSB_CUDA(cudaEventRecord(ws.ev2, s));
-	uint32_t hc[4];
-	SSB_CUDA(cudaMemcpyAsync(hc, ws.counters.get(), sizeof hc, cudaMemcpyDeviceToHost, s));
-	SSB_CUDA(cudaStreamSynchronize(s));
-	const uint32_t nDense = hc[1];
+
+	// CSR finalisation (compaction + gather of row ids / string addresses) is enqueued speculatively, before the host
+	// knows whether any query needs the dense path: the common case costs ONE host synchronisation for small batches
+	// (results copied at capacity together with the counters) and two for large ones (exact-size copy of the arrays).
+	const bool csr = hr && ix.K && hr->capQ >= nq && hr->capResults >= (size_t)nq * stride;
+	const bool small = (size_t)nq * stride <= 8192;
+	auto copy_arrays = [&](size_t total) {
+		SSB_CUDA(cudaMemcpyAsync(hr->kids, ws.csrKid.get(), total * 4, cudaMemcpyDeviceToHost, s));
+		SSB_CUDA(cudaMemcpyAsync(hr->scores, ws.csrScore.get(), total * 4, cudaMemcpyDeviceToHost, s));
+		SSB_CUDA(cudaMemcpyAsync(hr->rows, ws.csrRow.get(), total * 8, cudaMemcpyDeviceToHost, s));
+		SSB_CUDA(cudaMemcpyAsync(hr->strs, ws.csrStr.get(), total * 8, cudaMemcpyDeviceToHost, s));
+	};
+	auto enqueue_finalize = [&] {
+		k_clamp_counts<<<grid_for(nq), 256, 0, s>>>(ws.outCount.get(), nq, stride, ws.csrCount.get(), ws.counters.get() + 4);
+		SSB_LAUNCH_CHECK();
+		exclusive_scan_u32_u32(ws.csrCount.get(), ws.csrOff.get(), nq, ws.csrOff.get() + nq, s);
+		k_finalize_csr<<<grid_for((size_t)nq * 32), 256, 0, s>>>(ws.csrCount.get(), ws.csrOff.get(), ws.outKid.get(), ws.outScore.get(), nq,
+		                                                       stride, ix.keyOff.get(), ix.keyRow.get(), hr->strBase, (uint32_t)ix.unit,
+		                                                       ws.csrKid.get(), ws.csrScore.get(), ws.csrRow.get(), ws.csrStr.get());
+		SSB_LAUNCH_CHECK();
+		SSB_CUDA(cudaMemcpyAsync(hr->offsets, ws.csrOff.get(), (size_t)(nq + 1) * 4, cudaMemcpyDeviceToHost, s));
+		if (small) copy_arrays((size_t)nq * stride);
+	};
+	if (csr) enqueue_finalize();
+	uint32_t* hc = ws.hostCounters.get();
+	SSB_CUDA(cudaMemcpyAsync(hc, ws.counters.get(), 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+	SSB_CUDA(cudaEventRecord(ws.ev3, s));
+	SSB_CUDA(cudaEventSynchronize(ws.ev3));
+	const uint32_t nFast = hc[0], nDense = hc[1], nOverflow = hc[3];
+	unsigned long long postings;
+	memcpy(&postings, hc + 8, 8);
 	if (nDense) {
 		std::vector<uint32_t> dl(nDense);
 		SSB_CUDA(cudaMemcpyAsync(dl.data(), ws.denseList.get(), (size_t)nDense * 4, cudaMemcpyDeviceToHost, s));
@@ -568,14 +591,21 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 			SSB_CUDA(cudaStreamSynchronize(s));
 			run_dense_query<U>(ix, v, ws, d, q, threshold, limit, stride, out, s);
 		}
+		if (csr && out && out->big.empty()) {          // the dense queries changed the fixed-stride rows: finalise again
+			enqueue_finalize();
+			SSB_CUDA(cudaStreamSynchronize(s));
+		}
 	}
-	SSB_CUDA(cudaEventRecord(ws.ev3, s));
-	SSB_CUDA(cudaEventSynchronize(ws.ev3));
+	if (csr && out && out->big.empty()) {
+		if (!small) {
+			const size_t total = hr->offsets[nq];
+			if (total) { copy_arrays(total); SSB_CUDA(cudaStreamSynchronize(s)); }
+		}
+		out->csr = true;
+	}
 	if (st) {
-		unsigned long long sc[2];
-		SSB_CUDA(cudaMemcpy(sc, ws.statCounters.get(), sizeof sc, cudaMemcpyDeviceToHost));
-		st->nFast = hc[0]; st->nDense = nDense; st->nOverflow = hc[3];
-		st->postingsTouched = sc[0];
+		st->nFast = nFast; st->nDense = nDense; st->nOverflow = nOverflow;
+		st->postingsTouched = postings;
 		SSB_CUDA(cudaEventElapsedTime(&st->msDevice, ws.ev0, ws.ev3));
 		SSB_CUDA(cudaEventElapsedTime(&st->msFastKernel, ws.ev1, ws.ev2));
 	}
@@ -597,32 +627,10 @@ void search_batch(const DeviceIndex& ix, SearchWorkspace& ws, const void* qchars
 	ensure_workspace(ws, nq, charBytes, stride, s);
 	if (charBytes) SSB_CUDA(cudaMemcpyAsync(ws.qchars.get(), qchars, charBytes, cudaMemcpyHostToDevice, s));
 	SSB_CUDA(cudaMemcpyAsync(ws.qoff.get(), qoff, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
-	if (ix.unit == 1) run_device<uint8_t>(ix, ws, nq, threshold, limit, stride, &out, s, stats);
-	else run_device<uint32_t>(ix, ws, nq, threshold, limit, stride, &out, s, stats);
-	if (deviceOnly) return;          // sharded path: results stay in HBM for the cross-shard merge
-	if (hr && out.big.empty() && ix.K && hr->capQ >= nq && hr->capResults >= (size_t)nq * stride) {
-		// device-side CSR compaction + gather of row ids / string addresses, D2H straight into the caller's pinned arrays
-		uint32_t* anyBig = ws.counters.get() + 4;
-		k_clamp_counts<<<grid_for(nq), 256, 0, s>>>(ws.outCount.get(), nq, stride, ws.csrCount.get(), anyBig);
-		SSB_LAUNCH_CHECK();
-		exclusive_scan_u32_u32(ws.csrCount.get(), ws.csrOff.get(), nq, ws.csrOff.get() + nq, s);
-		k_finalize_csr<<<grid_for((size_t)nq * 32), 256, 0, s>>>(ws.csrCount.get(), ws.csrOff.get(), ws.outKid.get(), ws.outScore.get(), nq,
-		                                                       stride, ix.keyOff.get(), ix.keyRow.get(), hr->strBase, (uint32_t)ix.unit,
-		                                                       ws.csrKid.get(), ws.csrScore.get(), ws.csrRow.get(), ws.csrStr.get());
-		SSB_LAUNCH_CHECK();
-		SSB_CUDA(cudaMemcpyAsync(hr->offsets, ws.csrOff.get(), (size_t)(nq + 1) * 4, cudaMemcpyDeviceToHost, s));
-		SSB_CUDA(cudaStreamSynchronize(s));
-		const size_t total = hr->offsets[nq];
-		if (total) {
-			SSB_CUDA(cudaMemcpyAsync(hr->kids, ws.csrKid.get(), total * 4, cudaMemcpyDeviceToHost, s));
-			SSB_CUDA(cudaMemcpyAsync(hr->scores, ws.csrScore.get(), total * 4, cudaMemcpyDeviceToHost, s));
-			SSB_CUDA(cudaMemcpyAsync(hr->rows, ws.csrRow.get(), total * 8, cudaMemcpyDeviceToHost, s));
-			SSB_CUDA(cudaMemcpyAsync(hr->strs, ws.csrStr.get(), total * 8, cudaMemcpyDeviceToHost, s));
-			SSB_CUDA(cudaStreamSynchronize(s));
-		}
-		out.csr = true;
-		return;
-	}
+	HostResult* use = deviceOnly ? nullptr : hr;
+	if (ix.unit == 1) run_device<uint8_t>(ix, ws, nq, threshold, limit, stride, &out, s, stats, use);
+	else run_device<uint32_t>(ix, ws, nq, threshold, limit, stride, &out, s, stats, use);
+	if (deviceOnly || out.csr) return;          // sharded path: results stay in HBM; CSR path: already delivered into hr
 	out.kid.resize((size_t)nq * stride);
 	out.score.resize((size_t)nq * stride);
 	SSB_CUDA(cudaMemcpyAsync(out.count.data(), ws.outCount.get(), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
@@ -639,8 +647,8 @@ void search_batch_resident(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t 
 	if (!ix.indexed || nq == 0 || nq > ws.capQ) throw std::runtime_error("search_batch_resident: upload a batch with search_batch first");
 	const uint32_t stride = std::min<uint32_t>(limit, FAST_KLIM);
 	if (stride > ws.stride) throw std::runtime_error("search_batch_resident: limit larger than the uploaded batch's");
-	if (ix.unit == 1) run_device<uint8_t>(ix, ws, nq, threshold, limit, stride, nullptr, s, stats);
-	else run_device<uint32_t>(ix, ws, nq, threshold, limit, stride, nullptr, s, stats);
+	if (ix.unit == 1) run_device<uint8_t>(ix, ws, nq, threshold, limit, stride, nullptr, s, stats, nullptr);
+	else run_device<uint32_t>(ix, ws, nq, threshold, limit, stride, nullptr, s, stats, nullptr);
 }
 
 }   // namespace ssb

@@ -41,8 +41,11 @@ struct SearchWorkspace {
 	DevBuf<uint8_t> qchars, qnorm;
 	DevBuf<uint32_t> qoff;
 	DevBuf<QDesc> desc;
-	DevBuf<uint32_t> fastList, denseList, counters;   // counters: [0]=nFast [1]=nDense [2]=work cursor [3]=overflow count
-	DevBuf<unsigned long long> statCounters;          // [0]=postings touched [1]=candidates appended
+	DevBuf<uint32_t> fastList, denseList;
+	// [0]=nFast [1]=nDense [2]=work cursor [3]=overflow count [4]=any out-of-band list; [8..11] = two u64 statistics
+	// (postings touched, spare). One memset per batch, one async D2H into pinned hostCounters.
+	DevBuf<uint32_t> counters;
+	PinBuf<uint32_t> hostCounters;
 	// results (fixed stride)
 	DevBuf<uint32_t> outCount, outKid;
 	DevBuf<float> outScore;
