@@ -20,7 +20,8 @@ namespace {
 
 constexpr uint32_t INF = 0xFFFFFFFFu;
 constexpr int FS_THREADS = 128;
-constexpr int FS_WIN = 6144;                            // posting slots per staged pass
+constexpr int FS_WIN = 5632;                            // posting slots per staged pass
+constexpr int FS_DEF_CAP = 256;                         // deferred (term, count) pairs per pass: candidates whose evaluation needs edges / string compares
 constexpr int FS_REGION_PAD = 12;                        // per-list slack: 16-byte alignment shift (<=3) + bound slot + rounding
 constexpr int FS_WIN_ALLOC = FS_WIN + MAX_QGRAMS * FS_REGION_PAD + 16;
 constexpr int FS_BUF_MAX = 2 * FAST_KLIM;                // candidate buffer entries: 2 * limit rounded up to a power of two, chosen at launch
@@ -37,6 +38,8 @@ struct FastShared {
 	alignas(16) uint32_t win[FS_WIN_ALLOC];
 	unsigned long long* buf;                            // candidate buffer: bufCap entries behind this struct in dynamic smem
 	uint32_t bufCap;
+	unsigned long long deferred[FS_DEF_CAP];            // (count << 32 | term) pairs evaluated after the merge loop of the pass
+	uint32_t defCount;
 	alignas(8) unsigned long long bar;                  // mbarrier of the stage buffer (TMA completion)
 	uint32_t hist[256];
 	PassPlan plan;
@@ -51,6 +54,9 @@ struct FastShared {
 	uint32_t bufCount, overflow, query, selPrefixLo, selK;
 	uint32_t passLo, passHi, searchTop, cRej, lastPass, prefetched;
 	uint32_t qlen, nGrams, cmin, cprom, allOnes, nLists, total;
+	uint32_t shortActive, scanLong;    // the edit-distance path runs for this query / it also covers every long term
+	uint32_t scanLongOnly;             // internal: value_for_term() evaluates only the edit-distance path (unused, 0)
+	float threshold;
 	int topShift, kidBits;             // radix-select digit range (see select_smallest)
 	uint32_t classMode;                // 1: key high word = score-class rank (uniform weights), 0: ~ordered(score)
 	IndexView ix;
@@ -184,9 +190,70 @@ __device__ __forceinline__ void append_key(FastShared& sh, unsigned long long ke
 	if (idx < sh.bufCap) sh.buf[idx] = key; else sh.overflow = 1;
 }
 
-// A term reached `c` matches: evaluate its keys (hpp:310-341) and append what can still make the top-k.
+// Value that term t2 contributes to key `kid` through an edge of weight w2, over every path that applies to the term for
+// this query: the gram path for long terms (hpp:278-301) and the edit-distance path for short terms — and for long terms too
+// when |q| <= gSize (hpp:240-253). Returns -1 when the term does not reach the key (no hit / below the threshold).
+template <class U, bool SHORT>
+__device__ float value_for_term(FastShared& sh, const U* __restrict__ qn, uint32_t t2, uint32_t kid, float w2, int& keyEq)
+{
+	const IndexView& ix = sh.ix;
+	const uint32_t len2 = ix.termOff[t2 + 1] - ix.termOff[t2];
+	const bool isLong = len2 >= 2u * ix.g;
+	const float th = sh.threshold;
+	float best = -1.0f;
+	if (isLong && sh.nGrams >= 1 && !sh.scanLongOnly) {
+		const uint32_t c2 = count_for_term<U>(ix, t2, sh.qcode, sh.nGrams);
+		if (c2) {
+			const float s2 = sh.sOf[c2];
+			if (!(s2 < th)) {
+				float v = edge_value(w2, s2);
+				if (c2 >= sh.cprom) {
+					if (keyEq < 0) keyEq = key_equals_query<U>(ix, kid, qn, sh.qlen);
+					if (keyEq) v = 100.0f;
+				}
+				best = fmaxf(best, v);
+			}
+		}
+	}
+	if (SHORT && sh.shortActive && (!isLong || sh.scanLong)) {
+		const U* tc = reinterpret_cast<const U*>(ix.termChars) + ix.termOff[t2];
+		const uint32_t m2 = string_match<U>(qn, sh.qlen, tc, len2);
+		const float s2 = __fdiv_rn((float)m2, (float)sh.qlen);
+		if (!(s2 < th)) {
+			float v = edge_value(w2, s2);
+			if ((double)s2 > 0.999) {
+				if (keyEq < 0) keyEq = key_equals_query<U>(ix, kid, qn, sh.qlen);
+				if (keyEq) v = 100.0f;
+			}
+			best = fmaxf(best, v);
+		}
+	}
+	return best;
+}
+
+// Emits (kid, v) for the edge (term m -> kid) unless another edge of the same key gives it a better value: a key reachable
+// through several terms appears once, with its best value (per-key max-merge, hpp:326; ties -> smallest term id).
+template <class U, bool SHORT>
+__device__ void emit_edge(FastShared& sh, const U* __restrict__ qn, uint32_t m, uint32_t kid, float v, int keyEq)
+{
+	const IndexView& ix = sh.ix;
+	const unsigned long long key = rank_key(v, kid);
+	if (key >= sh.tau) return;
+	const uint32_t kb = ix.keyEdgeOff[kid], ke = ix.keyEdgeOff[kid + 1];
+	if (ke - kb > 1) {
+		for (uint32_t x = kb; x < ke; ++x) {
+			const uint32_t t2 = ix.keyEdgeTerm[x];
+			if (t2 == m) continue;
+			const float v2 = value_for_term<U, SHORT>(sh, qn, t2, kid, ix.keyEdgeW[x], keyEq);
+			if (v2 > v || (v2 == v && t2 < m)) return;           // dominated
+		}
+	}
+	append_key(sh, key);
+}
+
+// A long term reached `c` gram matches: evaluate its keys (hpp:310-341) and append what can still make the top-k.
 // Called only for terms that survive the integer pre-filter, i.e. rarely once tau is established -> not inlined.
-template <class U>
+template <class U, bool SHORT>
 __device__ __noinline__ void emit_candidate(FastShared& sh, const U* __restrict__ qn, uint32_t m, uint32_t c)
 {
 	const IndexView& ix = sh.ix;
@@ -201,34 +268,35 @@ __device__ __noinline__ void emit_candidate(FastShared& sh, const U* __restrict_
 		return;
 	}
 	const float s = sh.sOf[c];
-	const uint32_t cmin = sh.cmin, nGrams = sh.nGrams;
 	for (uint32_t e = ix.termEdgeOff[m]; e < ix.termEdgeOff[m + 1]; ++e) {           // hpp:321-338
 		const uint32_t kid = ix.edgeKid[e];
 		float v = edge_value(ix.edgeW[e], s);
-		const bool prom = c >= cprom && key_equals_query<U>(ix, kid, qn, qlen);
-		if (prom) v = 100.0f;
-		const unsigned long long key = rank_key(v, kid);
-		if (key >= tau) continue;
-		// a key reachable through several terms is emitted once, by the edge with the best value
-		// (per-key max-merge, hpp:326; ties -> smallest term id)
-		bool dominated = false;
-		const uint32_t kb = ix.keyEdgeOff[kid], ke = ix.keyEdgeOff[kid + 1];
-		for (uint32_t x = kb; x < ke && ke - kb > 1 && !dominated; ++x) {
-			const uint32_t t2 = ix.keyEdgeTerm[x];
-			if (t2 == m) continue;
-			const uint32_t c2 = count_for_term<U>(ix, t2, sh.qcode, nGrams);
-			if (c2 < cmin || c2 == 0) continue;
-			float v2 = edge_value(ix.keyEdgeW[x], sh.sOf[c2]);
-			if (c2 >= cprom && (prom || key_equals_query<U>(ix, kid, qn, qlen))) v2 = 100.0f;
-			dominated = v2 > v || (v2 == v && t2 < m);
+		int keyEq = -1;
+		if (c >= cprom) {
+			keyEq = key_equals_query<U>(ix, kid, qn, qlen);
+			if (keyEq) v = 100.0f;
 		}
-		if (dominated) continue;
-		append_key(sh, key);
+		emit_edge<U, SHORT>(sh, qn, m, kid, v, keyEq);
+	}
+}
+
+// Edit-distance path (hpp:232-254) for one term: every scanned term scores match/|q| (zeros included); when the scan covers
+// long terms (|q| <= gSize) their gram-path score is folded in here, so that a (term, key) pair is emitted exactly once.
+template <class U>
+__device__ __noinline__ void scan_term(FastShared& sh, const U* __restrict__ qn, uint32_t t)
+{
+	const IndexView& ix = sh.ix;
+	for (uint32_t e = ix.termEdgeOff[t]; e < ix.termEdgeOff[t + 1]; ++e) {
+		const uint32_t kid = ix.edgeKid[e];
+		int keyEq = -1;
+		const float v = value_for_term<U, true>(sh, qn, t, kid, ix.edgeW[e], keyEq);
+		if (v < 0.0f) continue;
+		emit_edge<U, true>(sh, qn, t, kid, v, keyEq);
 	}
 }
 
 // One pass over the staged windows: see the file comment.
-template <class U, int KT, bool ONES>
+template <class U, int KT, bool ONES, bool SHORT>
 __device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__ qn, uint32_t nLists)
 {
 	const int tid = threadIdx.x;
@@ -267,6 +335,12 @@ __device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__
 		const uint32_t nG = sh.nGrams;
 		while (cRej < nG && ((((unsigned long long)sh.hiKey[cRej + 1]) << 32) | lo) >= tau) ++cRej;
 	}
+	// The hot loop makes no calls: a surviving term is either appended right here (identity + uniform weights: kid == term id,
+	// value known from the count) or parked in the deferred list and evaluated after the loop (edges, weights, exact-match
+	// string compare, per-key max-merge). A call inside the loop costs the merge its registers (spilled heads).
+	const bool identMode = sh.ix.identity && sh.ix.uniformW;
+	const unsigned long long tauNow = sh.tau;
+	const uint32_t cpromNow = sh.cprom;
 	while (true) {
 		uint32_t m = head[0];
 #pragma unroll
@@ -299,32 +373,40 @@ __device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__
 				}
 			}
 		}
-		if (c > cRej) emit_candidate<U>(sh, qn, m, c);
+		if (c > cRej) {
+			if (identMode && c < cpromNow) {
+				const unsigned long long key = (((unsigned long long)sh.exactKey[c]) << 32) | m;
+				if (key < tauNow) append_key(sh, key);
+			} else {
+				const uint32_t di = atomicAdd(&sh.defCount, 1u);
+				if (di < FS_DEF_CAP) sh.deferred[di] = (((unsigned long long)c) << 32) | m; else sh.overflow = 1;
+			}
+		}
 	}
 }
 
-template <class U, bool ONES>
+template <class U, bool ONES, bool SHORT>
 __device__ __forceinline__ void merge_dispatch(FastShared& sh, const U* __restrict__ qn, uint32_t nLists)
 {
 	switch (nLists) {
-	case 1: merge_pass<U, 1, ONES>(sh, qn, nLists); break;
-	case 2: merge_pass<U, 2, ONES>(sh, qn, nLists); break;
-	case 3: merge_pass<U, 3, ONES>(sh, qn, nLists); break;
-	case 4: merge_pass<U, 4, ONES>(sh, qn, nLists); break;
-	case 5: merge_pass<U, 5, ONES>(sh, qn, nLists); break;
-	case 6: merge_pass<U, 6, ONES>(sh, qn, nLists); break;
-	case 7: merge_pass<U, 7, ONES>(sh, qn, nLists); break;
-	case 8: merge_pass<U, 8, ONES>(sh, qn, nLists); break;
-	case 9: merge_pass<U, 9, ONES>(sh, qn, nLists); break;
-	case 10: merge_pass<U, 10, ONES>(sh, qn, nLists); break;
-	case 11: merge_pass<U, 11, ONES>(sh, qn, nLists); break;
-	case 12: merge_pass<U, 12, ONES>(sh, qn, nLists); break;
-	case 13: merge_pass<U, 13, ONES>(sh, qn, nLists); break;
-	case 14: merge_pass<U, 14, ONES>(sh, qn, nLists); break;
-	case 15: case 16: merge_pass<U, 16, ONES>(sh, qn, nLists); break;
-	case 17: case 18: case 19: case 20: merge_pass<U, 20, ONES>(sh, qn, nLists); break;
-	case 21: case 22: case 23: case 24: merge_pass<U, 24, ONES>(sh, qn, nLists); break;
-	default: merge_pass<U, 32, ONES>(sh, qn, nLists); break;
+	case 1: merge_pass<U, 1, ONES, SHORT>(sh, qn, nLists); break;
+	case 2: merge_pass<U, 2, ONES, SHORT>(sh, qn, nLists); break;
+	case 3: merge_pass<U, 3, ONES, SHORT>(sh, qn, nLists); break;
+	case 4: merge_pass<U, 4, ONES, SHORT>(sh, qn, nLists); break;
+	case 5: merge_pass<U, 5, ONES, SHORT>(sh, qn, nLists); break;
+	case 6: merge_pass<U, 6, ONES, SHORT>(sh, qn, nLists); break;
+	case 7: merge_pass<U, 7, ONES, SHORT>(sh, qn, nLists); break;
+	case 8: merge_pass<U, 8, ONES, SHORT>(sh, qn, nLists); break;
+	case 9: merge_pass<U, 9, ONES, SHORT>(sh, qn, nLists); break;
+	case 10: merge_pass<U, 10, ONES, SHORT>(sh, qn, nLists); break;
+	case 11: merge_pass<U, 11, ONES, SHORT>(sh, qn, nLists); break;
+	case 12: merge_pass<U, 12, ONES, SHORT>(sh, qn, nLists); break;
+	case 13: merge_pass<U, 13, ONES, SHORT>(sh, qn, nLists); break;
+	case 14: merge_pass<U, 14, ONES, SHORT>(sh, qn, nLists); break;
+	case 15: case 16: merge_pass<U, 16, ONES, SHORT>(sh, qn, nLists); break;
+	case 17: case 18: case 19: case 20: merge_pass<U, 20, ONES, SHORT>(sh, qn, nLists); break;
+	case 21: case 22: case 23: case 24: merge_pass<U, 24, ONES, SHORT>(sh, qn, nLists); break;
+	default: merge_pass<U, 32, ONES, SHORT>(sh, qn, nLists); break;
 	}
 }
 
@@ -366,13 +448,15 @@ __device__ __forceinline__ bool plan_and_issue(FastShared& sh, uint32_t cur, uin
 	return true;
 }
 
-template <class U>
+// SHORT = the index has short terms, so queries shorter than 3*gSize also run the edit-distance scan; the lean variant
+// (no such terms, e.g. the benchmark vocabulary) is compiled without that code to keep the merge loops' registers.
+template <class U, bool SHORT>
 __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, const QDesc* __restrict__ desc, const U* __restrict__ qnorm,
                                                             const uint32_t* __restrict__ fastList, uint32_t* __restrict__ counters,
                                                             uint32_t* __restrict__ denseList, uint32_t limit, uint32_t outStride,
                                                             uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
                                                             float* __restrict__ outScore, unsigned long long* __restrict__ statCounters,
-                                                            uint32_t bufCap)
+                                                            uint32_t bufCap, float threshold)
 {
 	extern __shared__ __align__(16) unsigned char fs_smem[];
 	FastShared& sh = *reinterpret_cast<FastShared*>(fs_smem);
@@ -409,7 +493,8 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 		// identity + uniform weights: a candidate's value is fully determined by its match count, so the key's high word is the
 		// RANK of the score class (0 = exact match promoted to 100, then nGrams matches, ..., 1 match) instead of the float bits
 		// — same order, 8 significant bits for the radix select. Otherwise: ~ordered(float value).
-		const bool classMode = ix.identity && ix.uniformW;
+		const bool shortActive = SHORT && (d.flags & 1u) != 0, scanLong = SHORT && (d.flags & 2u) != 0;
+		const bool classMode = ix.identity && ix.uniformW && !shortActive;
 		if (tid <= MAX_QGRAMS) {
 			const uint32_t c = tid;
 			float s = (c <= nGrams && nGrams) ? term_score(c, nGrams) : 0.0f;
@@ -429,6 +514,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			sh.bufCount = 0; sh.overflow = 0; sh.tau = ~0ull; sh.passLo = 0; sh.prefetched = 0;
 			sh.qlen = d.qlen; sh.nGrams = nGrams; sh.cmin = d.cmin; sh.cprom = d.cprom; sh.nLists = nLists; sh.total = d.total;
 			sh.classMode = classMode;
+			sh.shortActive = shortActive; sh.scanLong = scanLong; sh.scanLongOnly = 0; sh.threshold = threshold;
 			sh.promotedKey = classMode ? 0u : ~float_to_ordered(100.0f);
 			sh.topShift = classMode ? 32 : 56;
 			int kb = 1;
@@ -440,10 +526,14 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 		}
 		__syncthreads();
 
-		bool failed = false, safeMode = false, more = nLists != 0;
+		// |q| <= gSize: the term scan below covers every long term and folds the gram path in, so no posting passes run
+		bool failed = false, safeMode = false, more = nLists != 0 && !scanLong;
 		uint32_t level = 0;
-		uint32_t cap = d.total > FS_FIRST_PASS ? FS_FIRST_PASS : FS_WIN;      // small first pass: it only has to establish tau
-		if (ix.identity && ix.uniformW && d.cmin <= 1 && k <= FAST_KLIM) {
+		// small first pass when tau cannot be seeded: it only has to establish tau, and every survivor of it is a candidate
+		// (identity mode: at most bufCap appends; otherwise at most FS_DEF_CAP deferred evaluations)
+		const uint32_t firstCap = (ix.identity && ix.uniformW) ? min((uint32_t)FS_FIRST_PASS, bufCap) : (uint32_t)FS_DEF_CAP;
+		uint32_t cap = d.total > firstCap ? firstCap : FS_WIN;
+		if (ix.identity && ix.uniformW && d.cmin <= 1 && k <= FAST_KLIM && more) {
 			// Seed tau without a pass: the first k postings of any one list are k distinct keys (kid == term id) with at least
 			// one match each, i.e. k candidates ranking at or before (score(1), kid = list[k-1]). The final k-th best cannot
 			// be worse, so everything behind the smallest such bound can be dropped from the start.
@@ -505,6 +595,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 						if (((((unsigned long long)sh.hiKey[c]) << 32) | lowKid) >= tau) rej = c; else break;
 					}
 					sh.cRej = rej;
+					sh.defCount = 0;
 					sh.lastPass = bound == INF;
 					if (best == 0) sh.overflow = 2;          // no list can advance (corrupt postings): never spin, fall back
 				}
@@ -512,9 +603,17 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			__syncthreads();
 			if (sh.overflow == 2) { failed = true; break; }
 			// ---- merge
-			if (sh.allOnes) merge_dispatch<U, true>(sh, qn, nLists);
-			else merge_dispatch<U, false>(sh, qn, nLists);
+			if (sh.allOnes) merge_dispatch<U, true, SHORT>(sh, qn, nLists);
+			else merge_dispatch<U, false, SHORT>(sh, qn, nLists);
 			__syncthreads();
+			{
+				const uint32_t nd = min(sh.defCount, (uint32_t)FS_DEF_CAP);
+				for (uint32_t i = tid; i < nd; i += FS_THREADS) {
+					const unsigned long long e = sh.deferred[i];
+					emit_candidate<U, SHORT>(sh, qn, (uint32_t)e, (uint32_t)(e >> 32));
+				}
+				if (nd) __syncthreads();
+			}
 			if (sh.overflow) {
 				// the optimistic pass overflowed the candidate buffer: roll it back, make room and redo it with a window small
 				// enough to be safe for single-edge terms; if that overflows too -> dense path
@@ -524,7 +623,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 				__syncthreads();
 				if (level > k) { select_smallest(sh, level, k); level = k; }
 				safeMode = true;
-				cap = min((uint32_t)FS_WIN, bufCap - level);
+				cap = min(min((uint32_t)FS_WIN, bufCap - level), (uint32_t)FS_DEF_CAP);
 				continue;
 			}
 			safeMode = false;
@@ -538,6 +637,20 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			// establish tau as soon as k candidates exist; afterwards the exact integer pre-filter keeps appends rare, so the
 			// (barrier-heavy) select only runs again when the buffer is half full
 			if (level > k && (sh.tau == ~0ull || level > bufCap / 2)) { select_smallest(sh, level, k); level = k; }
+		}
+		// ---- edit-distance path: brute-force scan of the short terms (and of all terms for |q| <= gSize), hpp:232-254
+		if (SHORT && !failed && shortActive) {
+			const uint32_t nScan = scanLong ? ix.T : ix.nShort;
+			for (uint32_t base = 0; base < nScan; base += FS_THREADS) {
+				const uint32_t i = base + tid;
+				if (i < nScan) scan_term<U>(sh, qn, scanLong ? i : ix.shortTerms[i]);
+				__syncthreads();
+				if (sh.overflow) { failed = true; break; }
+				level = sh.bufCount;
+				__syncthreads();
+				if (level > k && (sh.tau == ~0ull || level > bufCap / 2)) { select_smallest(sh, level, k); level = k; }
+			}
+			if (!failed) level = sh.bufCount;
 		}
 		if (failed) {
 			if (tid == 0) {

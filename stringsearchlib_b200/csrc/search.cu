@@ -118,6 +118,30 @@ __device__ uint32_t count_for_term(const IndexView& ix, uint32_t t, const uint64
 	return __popc(hits);
 }
 
+// stringMatch (hpp:182-222) restated column-wise: semi-global edit distance, free start and end in the source
+template <class U>
+__device__ uint32_t string_match(const U* __restrict__ q, uint32_t nq, const U* __restrict__ s, uint32_t ns)
+{
+	if (nq == 1) {
+		for (uint32_t j = 0; j < ns; ++j) if (s[j] == q[0]) return 1;
+		return 0;
+	}
+	uint32_t col[3 * MAX_GSIZE + 1];
+	for (uint32_t a = 0; a <= nq; ++a) col[a] = a;
+	uint32_t best = col[nq];
+	for (uint32_t j = 0; j < ns; ++j) {
+		uint32_t diag = col[0];          // D[a][j]
+		const U sc = s[j];
+		for (uint32_t a = 0; a < nq; ++a) {
+			uint32_t up = col[a + 1];    // D[a+1][j]
+			uint32_t v = min(min(col[a] + 1, up + 1), diag + (q[a] != sc ? 1u : 0u));
+			diag = up;
+			col[a + 1] = v;
+		}
+		best = min(best, col[nq]);
+	}
+	return nq - best;
+}
 // ---------------------------------------------------------------------------------------------- query prep
 template <class U>
 __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __restrict__ qchars, const uint32_t* __restrict__ qoff,
@@ -148,7 +172,9 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 	const bool shortActive = qlen < 3 * g && (ix.nShort > 0 || qlen <= g);           // hpp:381, 240-253
 	if (wildcard) cls = QC_WILDCARD;
 	else if (qlen == 0) cls = QC_EMPTY;                                               // hpp:374-375
-	else if (!shortActive && nGrams >= 1 && nGrams <= MAX_QGRAMS && limit <= FAST_KLIM) cls = QC_FAST;
+	// the fused kernel handles the edit-distance path only in its variant for indexes WITH short terms; on an index without
+	// them the path runs only for |q| <= gSize (scan of every long term), which is left to the dense path
+	else if ((nGrams >= 1 || shortActive) && (!shortActive || ix.nShort > 0) && nGrams <= MAX_QGRAMS && limit <= FAST_KLIM) cls = QC_FAST;
 	else cls = QC_DENSE;
 
 	uint32_t nLists = 0, total = 0;
@@ -193,6 +219,7 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 			if ((double)s > 0.999) cprom = c;                                         // hpp:328
 		}
 		d.cls = cls; d.qlen = qlen; d.nGrams = nGrams; d.nLists = nLists; d.cmin = cmin; d.cprom = cprom; d.total = total; d.qbeg = b;
+		d.flags = (shortActive ? 1u : 0u) | ((shortActive && qlen <= g) ? 2u : 0u);
 		outCount[q] = 0;
 		if (cls == QC_FAST) fastList[atomicAdd(&counters[0], 1u)] = q;
 		else if (cls == QC_DENSE || cls == QC_WILDCARD) denseList[atomicAdd(&counters[1], 1u)] = q;
@@ -303,30 +330,6 @@ __global__ void __launch_bounds__(256) k_dense_long(IndexView ix, const uint32_t
 	if (t >= ix.T) return;
 	uint32_t c = cnt[t];
 	if (c) dense_apply_term<U>(ix, t, term_score(c, nGrams), threshold, qn, qlen, entry);
-}
-// stringMatch (hpp:182-222) restated column-wise: semi-global edit distance, free start and end in the source
-template <class U>
-__device__ uint32_t string_match(const U* __restrict__ q, uint32_t nq, const U* __restrict__ s, uint32_t ns)
-{
-	if (nq == 1) {
-		for (uint32_t j = 0; j < ns; ++j) if (s[j] == q[0]) return 1;
-		return 0;
-	}
-	uint32_t col[3 * MAX_GSIZE + 1];
-	for (uint32_t a = 0; a <= nq; ++a) col[a] = a;
-	uint32_t best = col[nq];
-	for (uint32_t j = 0; j < ns; ++j) {
-		uint32_t diag = col[0];          // D[a][j]
-		const U sc = s[j];
-		for (uint32_t a = 0; a < nq; ++a) {
-			uint32_t up = col[a + 1];    // D[a+1][j]
-			uint32_t v = min(min(col[a] + 1, up + 1), diag + (q[a] != sc ? 1u : 0u));
-			diag = up;
-			col[a + 1] = v;
-		}
-		best = min(best, col[nq]);
-	}
-	return nq - best;
 }
 // short path (hpp:232-254): every short term, and every long term too when |q| <= gSize
 template <class U>
@@ -512,20 +515,27 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	while (bufCap < 2 * std::min<uint32_t>(limit, FAST_KLIM)) bufCap <<= 1;
 	const size_t smemBytes = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)bufCap * 8;
 	static int numSMs = 0;
-	static int ctasFor[3] = {0, 0, 0};
-	const int cfg = bufCap == 1024 ? 0 : (bufCap == 2048 ? 1 : 2);
+	static int ctasFor[6] = {0, 0, 0, 0, 0, 0};
+	const bool withShort = ix.nShort > 0;
+	const int cfg = (bufCap == 1024 ? 0 : (bufCap == 2048 ? 1 : 2)) + (withShort ? 3 : 0);
 	if (!numSMs) {
 		int dev = 0;
 		SSB_CUDA(cudaGetDevice(&dev));
 		SSB_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
 		const int maxSmem = (int)(((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)FS_BUF_MAX * 8);
-		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
 		SSB_CUDA(cudaFuncSetAttribute(k_order_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ORDER_MAX * 8)));
 	}
 	if (!ctasFor[cfg]) {
-		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasFor[cfg], k_fast_search<U>, FS_THREADS, smemBytes));
+		if (withShort) SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasFor[cfg], k_fast_search<U, true>, FS_THREADS, smemBytes));
+		else SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasFor[cfg], k_fast_search<U, false>, FS_THREADS, smemBytes));
 		if (ctasFor[cfg] < 1) ctasFor[cfg] = 1;
+		if (getenv("SSB_DEBUG"))
+			fprintf(stderr, "[ssb] k_fast_search: sizeof(FastShared)=%zu, bufCap=%u, dynamic smem=%zu B, %d CTAs/SM x %d threads (short-term variant: %d)\n",
+			        sizeof(FastShared), bufCap, smemBytes, ctasFor[cfg], FS_THREADS, (int)withShort);
 	}
 	const int ctasPerSM = ctasFor[cfg];
 	unsigned long long* statCounters = reinterpret_cast<unsigned long long*>(ws.counters.get() + 8);
@@ -544,9 +554,14 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	SSB_CUDA(cudaEventRecord(ws.ev1, s));
 	// persistent grid: one wave of resident CTAs (148 SMs x occupancy), queries handed out by an atomic cursor
 	const unsigned grid = (unsigned)std::min<size_t>((size_t)numSMs * ctasPerSM, std::max<uint32_t>(nq, 1));
-	k_fast_search<U><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(), ws.denseList.get(),
-	                                                     limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(),
-	                                                     statCounters, bufCap);
+	if (withShort)
+		k_fast_search<U, true><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(),
+		                                                           ws.denseList.get(), limit, stride, ws.outCount.get(), ws.outKid.get(),
+		                                                           ws.outScore.get(), statCounters, bufCap, threshold);
+	else
+		k_fast_search<U, false><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(),
+		                                                            ws.denseList.get(), limit, stride, ws.outCount.get(), ws.outKid.get(),
+		                                                            ws.outScore.get(), statCounters, bufCap, threshold);
 	SSB_LAUNCH_CHECK();
 	SSB_CUDA(cudaEventRecord(ws.ev2, s));
 

@@ -21,6 +21,8 @@ struct QDesc {
 	uint32_t cprom;       // smallest count c with (double)((float)c / (float)nGrams) > 0.999 (hpp:328)
 	uint32_t total;       // postings over all lists
 	uint32_t qbeg;        // offset of the normalised query in the qnorm buffer (units)
+	uint32_t flags;       // bit 0: the short (edit-distance) path runs (hpp:381); bit 1: it also scans every long term (hpp:247)
+	uint32_t pad;
 	uint32_t listOff[MAX_QGRAMS];
 	uint32_t listLen[MAX_QGRAMS];
 	uint64_t qcode[MAX_QGRAMS];   // code of every window (dups kept); ~0 = contains a symbol absent from the index
