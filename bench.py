@@ -315,6 +315,7 @@ def main():
             torch.cuda.synchronize()
 
     dev_ms, fast_ms, e2e_s, step_s, postings, results = [], [], [], [], [], []
+    last_st = {}
     sampler = ClockSampler(local_rank)
     launches0 = 0
     h2d = d2h = 0
@@ -353,6 +354,7 @@ def main():
             dev_ms.append(ms)
             fast_ms.append(msk)
             postings.append(st["postings"])
+            last_st = st
             results.append(n_results)
             assert st["nFast"] == args.batch and st["nDense"] == 0, st
             h2d = int(batches[s].offsets[-1]) + 4 * (args.batch + 1)
@@ -408,7 +410,11 @@ def main():
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(np.mean(e2e_s))},
             "gpu_launches": int(launches),   # kernels launched in the timed region (each step runs the path twice: e2e + resident)
-            "roofline": {"bound": "hbm", "kernel": "k_fast_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "queries_by_kernel": {"k_hash_search": last_st.get("nHash", 0), "k_fast_search": last_st.get("nHashHandover", 0),
+                                  "dense": last_st.get("nDense", 0)},
+            "roofline": {"bound": "hbm", "kernel": "k_hash_search" if last_st.get("nHash", 0) * 2 > args.batch else "k_fast_search",
+                         "timed": "k_hash_search + k_fast_search launches of one batch (CUDA events on the engine's stream)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms},
             "index_build": {"keys_per_s": args.keys / t_build, "seconds": t_build, "cold_first_build_seconds": t_build_cold,

@@ -292,10 +292,11 @@ class Index:
     def search_resident(self, nq, threshold=0.0, limit=100):
         """re-runs the device part of the last uploaded batch; returns (ms_device, ms_fast_kernel, stats dict)."""
         ms = (c_float * 2)()
-        st = (c_uint64 * 4)()
+        st = (c_uint64 * 8)()
         if self._lib.ssb_search_resident(self._h, nq, threshold, limit, ms, st) != 0:
             raise RuntimeError(self._lib.ssb_last_error().decode())
-        return ms[0], ms[1], dict(nFast=int(st[0]), nDense=int(st[1]), nOverflow=int(st[2]), postings=int(st[3]))
+        return ms[0], ms[1], dict(nFast=int(st[0]), nDense=int(st[1]), nOverflow=int(st[2]), postings=int(st[3]),
+                                  nHash=int(st[4]), nHashHandover=int(st[5]), nHashGiveUp=int(st[6]))
 
     def export_records_p2p(self, nq, limit, peer_recv, rank):
         """fused export + exchange: query q's records go straight into peer_recv[q // (nq/N)] (peer-mapped pointers)."""

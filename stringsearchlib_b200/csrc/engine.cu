@@ -498,7 +498,7 @@ SSB_API void ssb_batch_free(ssb_batch* b)
 	else { delete[] b->offsets; delete[] b->kids; delete[] b->scores; delete[] b->rows; delete[] b->strings; }
 	delete impl;
 }
-SSB_API int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uint32_t limit, float ms[2], uint64_t stats[4])
+SSB_API int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uint32_t limit, float ms[2], uint64_t stats[8])
 {
 	if (!ix) return -1;
 	return guarded([&] {
@@ -507,7 +507,10 @@ SSB_API int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uin
 		SearchStats st;
 		search_batch_resident(ix->dix, ix->ws, nq, threshold, limit, ix->stream, &st);
 		if (ms) { ms[0] = st.msDevice; ms[1] = st.msFastKernel; }
-		if (stats) { stats[0] = st.nFast; stats[1] = st.nDense; stats[2] = st.nOverflow; stats[3] = st.postingsTouched; }
+		if (stats) {
+			stats[0] = st.nFast; stats[1] = st.nDense; stats[2] = st.nOverflow; stats[3] = st.postingsTouched;
+			stats[4] = st.nHash; stats[5] = st.nHashHandover; stats[6] = st.nHashGiveUp; stats[7] = 0;
+		}
 		return 0;
 	}, -1);
 }

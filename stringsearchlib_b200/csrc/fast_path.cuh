@@ -110,7 +110,8 @@ __device__ __forceinline__ uint32_t lower_bound_smem(const uint32_t* a, uint32_t
 // keeps the k smallest entries of buf[0..n) (all distinct), sets tau to the k-th smallest. CTA-wide.
 // MSD radix select over 8-bit digits; digits known to be zero in every entry are skipped: the high word is a score-class
 // rank < 256 in uniform-weight mode (topShift = 32), and kids have kidBits significant bits.
-__device__ void select_smallest(FastShared& sh, uint32_t n, uint32_t k)
+template <int NT, class SH>
+__device__ void select_smallest(SH& sh, uint32_t n, uint32_t k)
 {
 	const int tid = threadIdx.x;
 	unsigned long long prefix = 0;
@@ -118,9 +119,9 @@ __device__ void select_smallest(FastShared& sh, uint32_t n, uint32_t k)
 	const int topShift = sh.topShift, kidBits = sh.kidBits;
 	for (int shift = topShift; shift >= 0; shift -= 8) {
 		if (shift < 32 && shift >= kidBits) { prefix <<= 8; continue; }      // this kid byte is zero everywhere
-		for (int i = tid; i < 256; i += FS_THREADS) sh.hist[i] = 0;
+		for (int i = tid; i < 256; i += NT) sh.hist[i] = 0;
 		__syncthreads();
-		for (uint32_t i = tid; i < n; i += FS_THREADS) {
+		for (uint32_t i = tid; i < n; i += NT) {
 			unsigned long long v = sh.buf[i];
 			if (shift == topShift || (v >> (shift + 8)) == prefix) atomicAdd(&sh.hist[(uint32_t)(v >> shift) & 255u], 1u);
 		}
@@ -146,9 +147,9 @@ __device__ void select_smallest(FastShared& sh, uint32_t n, uint32_t k)
 		prefix = (prefix << 8) | sh.selPrefixLo;
 		kk = sh.selK;
 	}
-	unsigned long long keep[FS_BUF_MAX / FS_THREADS];
+	unsigned long long keep[FS_BUF_MAX / NT];
 	uint32_t nk = 0;
-	for (uint32_t i = tid; i < n; i += FS_THREADS) {
+	for (uint32_t i = tid; i < n; i += NT) {
 		unsigned long long v = sh.buf[i];
 		if (v <= prefix) keep[nk++] = v;
 	}
@@ -159,15 +160,16 @@ __device__ void select_smallest(FastShared& sh, uint32_t n, uint32_t k)
 }
 
 // ascending bitonic sort of buf[0..n), n <= bufCap. CTA-wide.
-__device__ void sort_buffer(FastShared& sh, uint32_t n)
+template <int NT, class SH>
+__device__ void sort_buffer(SH& sh, uint32_t n)
 {
 	uint32_t p = 1;
 	while (p < n) p <<= 1;
-	for (uint32_t i = n + threadIdx.x; i < p; i += FS_THREADS) sh.buf[i] = ~0ull;
+	for (uint32_t i = n + threadIdx.x; i < p; i += NT) sh.buf[i] = ~0ull;
 	__syncthreads();
 	for (uint32_t size = 2; size <= p; size <<= 1)
 		for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-			for (uint32_t i = threadIdx.x; i < (p >> 1); i += FS_THREADS) {
+			for (uint32_t i = threadIdx.x; i < (p >> 1); i += NT) {
 				uint32_t lo = 2 * i - (i & (stride - 1));
 				uint32_t hi = lo + stride;
 				bool up = (lo & size) == 0;
@@ -179,7 +181,8 @@ __device__ void sort_buffer(FastShared& sh, uint32_t n)
 }
 
 // appends one key per calling lane; lanes that arrive together share one shared-memory atomic (opportunistic warp aggregation)
-__device__ __forceinline__ void append_key(FastShared& sh, unsigned long long key)
+template <class SH>
+__device__ __forceinline__ void append_key(SH& sh, unsigned long long key)
 {
 	const unsigned am = __activemask();
 	const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
@@ -193,8 +196,8 @@ __device__ __forceinline__ void append_key(FastShared& sh, unsigned long long ke
 // Value that term t2 contributes to key `kid` through an edge of weight w2, over every path that applies to the term for
 // this query: the gram path for long terms (hpp:278-301) and the edit-distance path for short terms — and for long terms too
 // when |q| <= gSize (hpp:240-253). Returns -1 when the term does not reach the key (no hit / below the threshold).
-template <class U, bool SHORT>
-__device__ float value_for_term(FastShared& sh, const U* __restrict__ qn, uint32_t t2, uint32_t kid, float w2, int& keyEq)
+template <class U, bool SHORT, class SH>
+__device__ float value_for_term(SH& sh, const U* __restrict__ qn, uint32_t t2, uint32_t kid, float w2, int& keyEq)
 {
 	const IndexView& ix = sh.ix;
 	const uint32_t len2 = ix.termOff[t2 + 1] - ix.termOff[t2];
@@ -233,8 +236,8 @@ __device__ float value_for_term(FastShared& sh, const U* __restrict__ qn, uint32
 
 // Emits (kid, v) for the edge (term m -> kid) unless another edge of the same key gives it a better value: a key reachable
 // through several terms appears once, with its best value (per-key max-merge, hpp:326; ties -> smallest term id).
-template <class U, bool SHORT>
-__device__ void emit_edge(FastShared& sh, const U* __restrict__ qn, uint32_t m, uint32_t kid, float v, int keyEq)
+template <class U, bool SHORT, class SH>
+__device__ void emit_edge(SH& sh, const U* __restrict__ qn, uint32_t m, uint32_t kid, float v, int keyEq)
 {
 	const IndexView& ix = sh.ix;
 	const unsigned long long key = rank_key(v, kid);
@@ -253,8 +256,8 @@ __device__ void emit_edge(FastShared& sh, const U* __restrict__ qn, uint32_t m, 
 
 // A long term reached `c` gram matches: evaluate its keys (hpp:310-341) and append what can still make the top-k.
 // Called only for terms that survive the integer pre-filter, i.e. rarely once tau is established -> not inlined.
-template <class U, bool SHORT>
-__device__ __noinline__ void emit_candidate(FastShared& sh, const U* __restrict__ qn, uint32_t m, uint32_t c)
+template <class U, bool SHORT, class SH>
+__device__ __noinline__ void emit_candidate(SH& sh, const U* __restrict__ qn, uint32_t m, uint32_t c)
 {
 	const IndexView& ix = sh.ix;
 	const unsigned long long tau = sh.tau;
@@ -412,7 +415,8 @@ __device__ __forceinline__ void merge_dispatch(FastShared& sh, const U* __restri
 
 // warp 0: lays out the windows of one pass in the stage buffer from the cursors (cur, rem) and issues the TMA copies.
 // Returns (uniformly over the warp) whether anything was issued.
-__device__ __forceinline__ bool plan_and_issue(FastShared& sh, uint32_t cur, uint32_t rem, uint32_t cap, const uint32_t* postings, int lane)
+template <class SH>
+__device__ __forceinline__ bool plan_and_issue(SH& sh, uint32_t cur, uint32_t rem, uint32_t cap, const uint32_t* postings, int lane)
 {
 	const uint32_t nLists = sh.nLists;
 	const uint32_t wmax = max(1u, cap / nLists);
@@ -456,12 +460,14 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
                                                             uint32_t* __restrict__ denseList, uint32_t limit, uint32_t outStride,
                                                             uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
                                                             float* __restrict__ outScore, unsigned long long* __restrict__ statCounters,
-                                                            uint32_t bufCap, float threshold)
+                                                            uint32_t bufCap, float threshold, uint32_t nIdx, uint32_t curIdx)
 {
+	// nIdx / curIdx: which counters hold this launch's list length and work cursor (the list is either every fast query or
+	// the ones k_hash_search handed over)
 	extern __shared__ __align__(16) unsigned char fs_smem[];
 	FastShared& sh = *reinterpret_cast<FastShared*>(fs_smem);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t nFast = counters[0];
+	const uint32_t nFast = counters[nIdx];
 	const uint32_t k = limit;
 	if (tid == 0) {
 		sh.win[FS_WIN_ALLOC - 1] = INF;
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 
 	while (true) {
 		__syncthreads();
-		if (tid == 0) sh.query = atomicAdd(&counters[2], 1u);
+		if (tid == 0) sh.query = atomicAdd(&counters[curIdx], 1u);
 		__syncthreads();
 		const uint32_t wi = sh.query;
 		if (wi >= nFast) break;
@@ -621,7 +627,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 				__syncthreads();
 				if (tid == 0) { sh.bufCount = level; sh.overflow = 0; }
 				__syncthreads();
-				if (level > k) { select_smallest(sh, level, k); level = k; }
+				if (level > k) { select_smallest<FS_THREADS>(sh, level, k); level = k; }
 				safeMode = true;
 				cap = min(min((uint32_t)FS_WIN, bufCap - level), (uint32_t)FS_DEF_CAP);
 				continue;
@@ -636,7 +642,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			if (tid == 0) sh.passLo = nextLo;
 			// establish tau as soon as k candidates exist; afterwards the exact integer pre-filter keeps appends rare, so the
 			// (barrier-heavy) select only runs again when the buffer is half full
-			if (level > k && (sh.tau == ~0ull || level > bufCap / 2)) { select_smallest(sh, level, k); level = k; }
+			if (level > k && (sh.tau == ~0ull || level > bufCap / 2)) { select_smallest<FS_THREADS>(sh, level, k); level = k; }
 		}
 		// ---- edit-distance path: brute-force scan of the short terms (and of all terms for |q| <= gSize), hpp:232-254
 		if (SHORT && !failed && shortActive) {
@@ -648,7 +654,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 				if (sh.overflow) { failed = true; break; }
 				level = sh.bufCount;
 				__syncthreads();
-				if (level > k && (sh.tau == ~0ull || level > bufCap / 2)) { select_smallest(sh, level, k); level = k; }
+				if (level > k && (sh.tau == ~0ull || level > bufCap / 2)) { select_smallest<FS_THREADS>(sh, level, k); level = k; }
 			}
 			if (!failed) level = sh.bufCount;
 		}
@@ -660,8 +666,8 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			continue;
 		}
 		// ---- final: top-k, sorted
-		if (level > k) { select_smallest(sh, level, k); level = k; }
-		sort_buffer(sh, level);
+		if (level > k) { select_smallest<FS_THREADS>(sh, level, k); level = k; }
+		sort_buffer<FS_THREADS>(sh, level);
 		for (uint32_t i = tid; i < level; i += FS_THREADS) {
 			unsigned long long v = sh.buf[i];
 			outKid[(size_t)q * outStride + i] = (uint32_t)v;

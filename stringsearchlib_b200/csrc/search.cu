@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 }   // namespace
 
 #include "fast_path.cuh"   // k_fast_search (inside namespace ssb)
+#include "hash_path.cuh"   // k_hash_search
 
 namespace {
 
@@ -492,7 +493,7 @@ void ensure_workspace(SearchWorkspace& ws, uint32_t nq, size_t charBytes, uint32
 	}
 	if (nq > ws.capQ || stride > ws.stride) {
 		uint32_t cq = std::max(nq, ws.capQ), st = std::max(stride, ws.stride);
-		ws.qoff.alloc(cq + 1, s); ws.desc.alloc(cq, s); ws.fastList.alloc(cq, s); ws.denseList.alloc(cq, s);
+		ws.qoff.alloc(cq + 1, s); ws.desc.alloc(cq, s); ws.fastList.alloc(cq, s); ws.fastList2.alloc(cq, s); ws.denseList.alloc(cq, s);
 		ws.outCount.alloc(cq, s); ws.outKid.alloc((size_t)cq * st, s); ws.outScore.alloc((size_t)cq * st, s);
 		ws.csrCount.alloc(cq + 1, s); ws.csrOff.alloc(cq + 1, s); ws.csrKid.alloc((size_t)cq * st, s); ws.csrScore.alloc((size_t)cq * st, s);
 		ws.csrRow.alloc((size_t)cq * st, s); ws.csrStr.alloc((size_t)cq * st, s);
@@ -552,16 +553,39 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		SSB_LAUNCH_CHECK();
 	}
 	SSB_CUDA(cudaEventRecord(ws.ev1, s));
-	// persistent grid: one wave of resident CTAs (148 SMs x occupancy), queries handed out by an atomic cursor
+	// persistent grids: one wave of resident CTAs, queries handed out by an atomic cursor. k_hash_search takes the fast queries
+	// first (limit <= 512) and hands the ones it cannot answer to k_fast_search through fastList2.
+	static const bool noHash = getenv("SSB_HASH") == nullptr;   // opt-in until it beats the merge kernel
+	const bool useHash = !noHash && limit <= (uint32_t)HS_KLIM;
+	if (useHash) {
+		static int hashCtas = 0;
+		const size_t hsBytes = ((sizeof(HashShared) + 15) & ~size_t(15)) + (size_t)1024 * 8;
+		if (!hashCtas) {
+			SSB_CUDA(cudaFuncSetAttribute(k_hash_search<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsBytes));
+			SSB_CUDA(cudaFuncSetAttribute(k_hash_search<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsBytes));
+			SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hashCtas, k_hash_search<U>, HS_THREADS, hsBytes));
+			if (hashCtas < 1) hashCtas = 1;
+			if (getenv("SSB_DEBUG"))
+				fprintf(stderr, "[ssb] k_hash_search: sizeof(HashShared)=%zu, dynamic smem=%zu B, %d CTAs/SM x %d threads\n",
+				        sizeof(HashShared), hsBytes, hashCtas, HS_THREADS);
+		}
+		const unsigned hgrid = (unsigned)std::min<size_t>((size_t)numSMs * hashCtas, std::max<uint32_t>(nq, 1));
+		k_hash_search<U><<<hgrid, HS_THREADS, hsBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(), ws.fastList2.get(),
+		                                                    limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(),
+		                                                    statCounters, 1024u, threshold);
+		SSB_LAUNCH_CHECK();
+	}
+	const uint32_t* fl = useHash ? ws.fastList2.get() : ws.fastList.get();
+	const uint32_t nIdx = useHash ? 5u : 0u, curIdx = useHash ? 12u : 2u;
 	const unsigned grid = (unsigned)std::min<size_t>((size_t)numSMs * ctasPerSM, std::max<uint32_t>(nq, 1));
 	if (withShort)
-		k_fast_search<U, true><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(),
+		k_fast_search<U, true><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, fl, ws.counters.get(),
 		                                                           ws.denseList.get(), limit, stride, ws.outCount.get(), ws.outKid.get(),
-		                                                           ws.outScore.get(), statCounters, bufCap, threshold);
+		                                                           ws.outScore.get(), statCounters, bufCap, threshold, nIdx, curIdx);
 	else
-		k_fast_search<U, false><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(),
+		k_fast_search<U, false><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, fl, ws.counters.get(),
 		                                                            ws.denseList.get(), limit, stride, ws.outCount.get(), ws.outKid.get(),
-		                                                            ws.outScore.get(), statCounters, bufCap, threshold);
+		                                                            ws.outScore.get(), statCounters, bufCap, threshold, nIdx, curIdx);
 	SSB_LAUNCH_CHECK();
 	SSB_CUDA(cudaEventRecord(ws.ev2, s));
 
@@ -620,6 +644,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	}
 	if (st) {
 		st->nFast = nFast; st->nDense = nDense; st->nOverflow = nOverflow;
+		st->nHash = hc[6]; st->nHashHandover = hc[5]; st->nHashGiveUp = hc[7];
 		st->postingsTouched = postings;
 		SSB_CUDA(cudaEventElapsedTime(&st->msDevice, ws.ev0, ws.ev3));
 		SSB_CUDA(cudaEventElapsedTime(&st->msFastKernel, ws.ev1, ws.ev2));

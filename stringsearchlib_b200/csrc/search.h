@@ -31,6 +31,7 @@ struct QDesc {
 
 struct SearchStats {
 	uint32_t nFast = 0, nDense = 0, nWildcard = 0, nEmpty = 0, nOverflow = 0;
+	uint32_t nHash = 0, nHashHandover = 0, nHashGiveUp = 0;   // k_hash_search: answered / handed to k_fast_search / of those, given up mid-query
 	uint64_t postingsTouched = 0;   // sum over fast queries of posting-list lengths (algorithmic bytes / 4)
 	uint64_t candidates = 0;
 	float msDevice = 0;             // CUDA-event time of the device part of the last batch
@@ -43,8 +44,9 @@ struct SearchWorkspace {
 	DevBuf<uint8_t> qchars, qnorm;
 	DevBuf<uint32_t> qoff;
 	DevBuf<QDesc> desc;
-	DevBuf<uint32_t> fastList, denseList;
-	// [0]=nFast [1]=nDense [2]=work cursor [3]=overflow count [4]=any out-of-band list; [8..11] = two u64 statistics
+	DevBuf<uint32_t> fastList, fastList2, denseList;   // fastList2: queries k_hash_search hands to k_fast_search
+	// [0]=nFast [1]=nDense [2]=work cursor [3]=overflow count [4]=any out-of-band list [5]=handed to k_fast_search
+	// [6]=answered by k_hash_search [7]=of [5], given up mid-query [12]=k_fast_search cursor; [8..11] = two u64 statistics
 	// (postings touched, spare). One memset per batch, one async D2H into pinned hostCounters.
 	DevBuf<uint32_t> counters;
 	PinBuf<uint32_t> hostCounters;
