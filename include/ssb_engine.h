@@ -16,6 +16,10 @@ const char* ssb_last_error(void);
 uint64_t ssb_kernel_launches(void);
 /* binds the engine to a CUDA device (default: current device). Call once per process, before any index. */
 int ssb_set_device(int device);
+/* which kernel answers the batched fast path first: 0 = k_fast_search (register K-way merge of the posting lists; default),
+ * 1 = k_hash_search (duplicate detection by shared-memory hashing, falls back to 0 per query). Results are identical;
+ * the switch exists for measurements and for the parity tests that cover both. 0 on success. */
+int ssb_set_search_path(int path);
 
 /* ---- index build: replaces StringIndex::StringIndex (nGramSearch.hpp:120-172) ----
  * words: size pointers to NUL-terminated strings of char (wide=0) or wchar_t/UTF-32 (wide=1), NULL allowed;

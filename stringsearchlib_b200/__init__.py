@@ -6,4 +6,4 @@ surface). This package is only a thin ctypes mirror of those C ABIs for tests an
 fallback: importing works without a GPU (so that symbols can be checked), every compute call needs a B200.
 """
 from .api import (GuidLibrary, HandleLibrary, Index, SearchResult, core_library, kernel_launches, lib_path,  # noqa: F401
-                  set_device)
+                  set_device, set_search_path)

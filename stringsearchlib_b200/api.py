@@ -39,6 +39,7 @@ def core_library():
     lib.ssb_last_error.restype = c_char_p
     lib.ssb_kernel_launches.restype = c_uint64
     lib.ssb_set_device.argtypes = [c_int]
+    lib.ssb_set_search_path.argtypes = [c_int]
     lib.ssb_index_create.restype = c_void_p
     lib.ssb_index_create.argtypes = [POINTER(c_void_p), c_uint64, c_uint16, POINTER(c_float), c_uint16, c_int, c_uint64]
     lib.ssb_index_create_packed.restype = c_void_p
@@ -78,6 +79,12 @@ def core_library():
 
 def kernel_launches():
     return int(core_library().ssb_kernel_launches())
+
+
+def set_search_path(path):
+    """0 = k_fast_search first (default), 1 = k_hash_search first; identical results (include/ssb_engine.h)."""
+    if core_library().ssb_set_search_path(int(path)) != 0:
+        raise ValueError("search path must be 0 or 1")
 
 
 def set_device(device):

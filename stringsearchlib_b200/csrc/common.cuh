@@ -28,6 +28,9 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 // every kernel launch of the engine goes through SSB_LAUNCH_CHECK(): it validates the launch and counts it
 // (ssb_kernel_launches() feeds bench.py's "gpu_launches")
 inline std::atomic<uint64_t> g_kernel_launches{0};
+// which kernel answers the fast queries first: 0 = k_fast_search (register K-way merge), 1 = k_hash_search (duplicate detection
+// by hashing; hands what it cannot take to k_fast_search). Both are exact; see DESIGN.md for why the merge is the default.
+inline std::atomic<int> g_search_path{-1};       // -1: not set -> environment SSB_HASH=1 selects 1, else 0
 #define SSB_LAUNCH_CHECK() (::ssb::g_kernel_launches.fetch_add(1, std::memory_order_relaxed), \
                             ::ssb::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__))
 

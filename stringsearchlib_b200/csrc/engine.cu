@@ -330,6 +330,12 @@ extern "C" {
 
 SSB_API const char* ssb_last_error(void) { return g_lastError.c_str(); }
 SSB_API uint64_t ssb_kernel_launches(void) { return g_kernel_launches.load(); }
+SSB_API int ssb_set_search_path(int path)
+{
+	if (path < 0 || path > 1) return -1;
+	g_search_path.store(path);
+	return 0;
+}
 SSB_API int ssb_set_device(int device)
 {
 	return guarded([&] { g_engine.device = device; g_engine.init(); return 0; }, -1);

@@ -20,8 +20,8 @@ namespace {
 
 constexpr uint32_t INF = 0xFFFFFFFFu;
 constexpr int FS_THREADS = 128;
-constexpr int FS_WIN = 5632;                            // posting slots per staged pass
-constexpr int FS_DEF_CAP = 256;                         // deferred (term, count) pairs per pass: candidates whose evaluation needs edges / string compares
+constexpr int FS_WIN = 6144;                            // posting slots per staged pass
+constexpr int FS_DEF_CAP = 128;                         // deferred (term, count) pairs per pass: candidates whose evaluation needs edges / string compares
 constexpr int FS_REGION_PAD = 12;                        // per-list slack: 16-byte alignment shift (<=3) + bound slot + rounding
 constexpr int FS_WIN_ALLOC = FS_WIN + MAX_QGRAMS * FS_REGION_PAD + 16;
 constexpr int FS_BUF_MAX = 2 * FAST_KLIM;                // candidate buffer entries: 2 * limit rounded up to a power of two, chosen at launch
@@ -38,10 +38,12 @@ struct FastShared {
 	alignas(16) uint32_t win[FS_WIN_ALLOC];
 	unsigned long long* buf;                            // candidate buffer: bufCap entries behind this struct in dynamic smem
 	uint32_t bufCap;
-	unsigned long long deferred[FS_DEF_CAP];            // (count << 32 | term) pairs evaluated after the merge loop of the pass
 	uint32_t defCount;
 	alignas(8) unsigned long long bar;                  // mbarrier of the stage buffer (TMA completion)
-	uint32_t hist[256];
+	union {
+		unsigned long long deferred[FS_DEF_CAP];        // (count << 32 | term) pairs: live from the merge loop of a pass to the evaluation right after it
+		uint32_t hist[256];                             // live inside select_smallest
+	};
 	PassPlan plan;
 	uint32_t cur[MAX_QGRAMS], rem[MAX_QGRAMS], nTake[MAX_QGRAMS], mult[MAX_QGRAMS], listOff[MAX_QGRAMS];
 	uint32_t winByte[MAX_QGRAMS];                        // byte offset of list i's window from &win[0] (current pass)
@@ -107,10 +109,18 @@ __device__ __forceinline__ uint32_t lower_bound_smem(const uint32_t* a, uint32_t
 	return lo;
 }
 
+// barrier of the NT threads that call it: the whole CTA (BAR == 0) or a named barrier shared by a subset of its warps
+template <int BAR, int NT>
+__device__ __forceinline__ void group_sync()
+{
+	if (BAR == 0) __syncthreads();
+	else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory");
+}
+
 // keeps the k smallest entries of buf[0..n) (all distinct), sets tau to the k-th smallest. CTA-wide.
 // MSD radix select over 8-bit digits; digits known to be zero in every entry are skipped: the high word is a score-class
 // rank < 256 in uniform-weight mode (topShift = 32), and kids have kidBits significant bits.
-template <int NT, class SH>
+template <int NT, int BAR = 0, class SH>
 __device__ void select_smallest(SH& sh, uint32_t n, uint32_t k)
 {
 	const int tid = threadIdx.x;
@@ -120,12 +130,12 @@ __device__ void select_smallest(SH& sh, uint32_t n, uint32_t k)
 	for (int shift = topShift; shift >= 0; shift -= 8) {
 		if (shift < 32 && shift >= kidBits) { prefix <<= 8; continue; }      // this kid byte is zero everywhere
 		for (int i = tid; i < 256; i += NT) sh.hist[i] = 0;
-		__syncthreads();
+		group_sync<BAR, NT>();
 		for (uint32_t i = tid; i < n; i += NT) {
 			unsigned long long v = sh.buf[i];
 			if (shift == topShift || (v >> (shift + 8)) == prefix) atomicAdd(&sh.hist[(uint32_t)(v >> shift) & 255u], 1u);
 		}
-		__syncthreads();
+		group_sync<BAR, NT>();
 		if (tid < 32) {
 			uint32_t loc[8], sum = 0;
 #pragma unroll
@@ -143,7 +153,7 @@ __device__ void select_smallest(SH& sh, uint32_t n, uint32_t k)
 				}
 			}
 		}
-		__syncthreads();
+		group_sync<BAR, NT>();
 		prefix = (prefix << 8) | sh.selPrefixLo;
 		kk = sh.selK;
 	}
@@ -154,19 +164,19 @@ __device__ void select_smallest(SH& sh, uint32_t n, uint32_t k)
 		if (v <= prefix) keep[nk++] = v;
 	}
 	if (tid == 0) { sh.bufCount = 0; sh.tau = prefix; }
-	__syncthreads();
+	group_sync<BAR, NT>();
 	for (uint32_t j = 0; j < nk; ++j) sh.buf[atomicAdd(&sh.bufCount, 1u)] = keep[j];
-	__syncthreads();
+	group_sync<BAR, NT>();
 }
 
 // ascending bitonic sort of buf[0..n), n <= bufCap. CTA-wide.
-template <int NT, class SH>
+template <int NT, int BAR = 0, class SH>
 __device__ void sort_buffer(SH& sh, uint32_t n)
 {
 	uint32_t p = 1;
 	while (p < n) p <<= 1;
 	for (uint32_t i = n + threadIdx.x; i < p; i += NT) sh.buf[i] = ~0ull;
-	__syncthreads();
+	group_sync<BAR, NT>();
 	for (uint32_t size = 2; size <= p; size <<= 1)
 		for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
 			for (uint32_t i = threadIdx.x; i < (p >> 1); i += NT) {
@@ -176,7 +186,7 @@ __device__ void sort_buffer(SH& sh, uint32_t n)
 				unsigned long long a = sh.buf[lo], b = sh.buf[hi];
 				if ((a > b) == up) { sh.buf[lo] = b; sh.buf[hi] = a; }
 			}
-			__syncthreads();
+			group_sync<BAR, NT>();
 		}
 }
 
@@ -534,6 +544,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 
 		// |q| <= gSize: the term scan below covers every long term and folds the gram path in, so no posting passes run
 		bool failed = false, safeMode = false, more = nLists != 0 && !scanLong;
+		bool tauReal = false;          // tau comes from a select over real candidates (not merely from the seed below)
 		uint32_t level = 0;
 		// small first pass when tau cannot be seeded: it only has to establish tau, and every survivor of it is a candidate
 		// (identity mode: at most bufCap appends; otherwise at most FS_DEF_CAP deferred evaluations)
@@ -550,7 +561,9 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 				if (lane == 0 && x != INF) sh.tau = ((((unsigned long long)sh.exactKey[1]) << 32) | x) + 1;   // "< tau" keeps the bound itself
 			}
 			__syncthreads();
-			if (sh.tau != ~0ull) cap = FS_WIN;
+			// a seeded tau admits ~k single-list terms per list; a short first pass (about 3k postings) finds k real candidates
+			// among the smallest ids, the select that follows it replaces the seed by a bound that is ~nLists times tighter
+			if (sh.tau != ~0ull) cap = min((uint32_t)FS_WIN, max(3u * k, 256u));
 		}
 		while (more) {
 			// ---- warp 0: lay out the windows from the cursors and issue the TMA copies
@@ -627,9 +640,11 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 				__syncthreads();
 				if (tid == 0) { sh.bufCount = level; sh.overflow = 0; }
 				__syncthreads();
-				if (level > k) { select_smallest<FS_THREADS>(sh, level, k); level = k; }
+				if (level > k) { select_smallest<FS_THREADS>(sh, level, k); level = k; tauReal = true; }
 				safeMode = true;
-				cap = min(min((uint32_t)FS_WIN, bufCap - level), (uint32_t)FS_DEF_CAP);
+				// (uniform weights + kid == term id: survivors are appended directly, only exact-match suspects are deferred)
+				cap = min((uint32_t)FS_WIN, bufCap - level);
+				if (!(ix.identity && ix.uniformW)) cap = min(cap, (uint32_t)FS_DEF_CAP);
 				continue;
 			}
 			safeMode = false;
@@ -642,7 +657,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			if (tid == 0) sh.passLo = nextLo;
 			// establish tau as soon as k candidates exist; afterwards the exact integer pre-filter keeps appends rare, so the
 			// (barrier-heavy) select only runs again when the buffer is half full
-			if (level > k && (sh.tau == ~0ull || level > bufCap / 2)) { select_smallest<FS_THREADS>(sh, level, k); level = k; }
+			if (level > k && (!tauReal || level > bufCap / 2)) { select_smallest<FS_THREADS>(sh, level, k); level = k; tauReal = true; }
 		}
 		// ---- edit-distance path: brute-force scan of the short terms (and of all terms for |q| <= gSize), hpp:232-254
 		if (SHORT && !failed && shortActive) {
@@ -654,7 +669,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 				if (sh.overflow) { failed = true; break; }
 				level = sh.bufCount;
 				__syncthreads();
-				if (level > k && (sh.tau == ~0ull || level > bufCap / 2)) { select_smallest<FS_THREADS>(sh, level, k); level = k; }
+				if (level > k && (!tauReal || level > bufCap / 2)) { select_smallest<FS_THREADS>(sh, level, k); level = k; tauReal = true; }
 			}
 			if (!failed) level = sh.bufCount;
 		}

@@ -555,8 +555,9 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	SSB_CUDA(cudaEventRecord(ws.ev1, s));
 	// persistent grids: one wave of resident CTAs, queries handed out by an atomic cursor. k_hash_search takes the fast queries
 	// first (limit <= 512) and hands the ones it cannot answer to k_fast_search through fastList2.
-	static const bool noHash = getenv("SSB_HASH") == nullptr;   // opt-in until it beats the merge kernel
-	const bool useHash = !noHash && limit <= (uint32_t)HS_KLIM;
+	static const bool envHash = getenv("SSB_HASH") != nullptr;
+	const int pathOpt = g_search_path.load(std::memory_order_relaxed);
+	const bool useHash = (pathOpt < 0 ? envHash : pathOpt == 1) && limit <= (uint32_t)HS_KLIM;
 	if (useHash) {
 		static int hashCtas = 0;
 		const size_t hsBytes = ((sizeof(HashShared) + 15) & ~size_t(15)) + (size_t)1024 * 8;
@@ -645,6 +646,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	if (st) {
 		st->nFast = nFast; st->nDense = nDense; st->nOverflow = nOverflow;
 		st->nHash = hc[6]; st->nHashHandover = hc[5]; st->nHashGiveUp = hc[7];
+		if (hc[7] && getenv("SSB_DEBUG")) fprintf(stderr, "[ssb] k_hash_search gave up on %u queries: buffer %u, queue %u, other %u\n", hc[7], hc[13], hc[14], hc[15]);
 		st->postingsTouched = postings;
 		SSB_CUDA(cudaEventElapsedTime(&st->msDevice, ws.ev0, ws.ev3));
 		SSB_CUDA(cudaEventElapsedTime(&st->msFastKernel, ws.ev1, ws.ev2));

@@ -55,19 +55,28 @@ def check_tables(ix, S):
 
 
 def check_search(ix, S, queries, threshold, limit, o=None):
+    """every batch is answered twice — k_fast_search first (path 0, the default) and k_hash_search first (path 1) — and
+    both must equal the oracle bit for bit"""
+    import stringsearchlib_b200 as m
     o = o or S.tables()
-    r = ix.search_batch(queries, threshold, limit)
     counts, ext, sc = S.search_batch(queries, threshold, limit)
     nq = len(queries)
-    assert len(r) == nq
-    got_counts = np.diff(r.offsets)
-    assert np.array_equal(got_counts, counts), np.nonzero(got_counts != counts)[0][:10]
     kid_of_ext = o["kidOfExt"]
-    for q in range(nq):
-        n = int(counts[q])
-        kids, scores, _, _ = r.query(q)
-        assert np.array_equal(scores.view(np.uint32), sc[q, :n].view(np.uint32)), (q, scores[:8], sc[q, :8])
-        assert np.array_equal(kids, kid_of_ext[ext[q, :n]]), (q, kids[:8], kid_of_ext[ext[q, :8]])
+    r = None
+    try:
+        for path in (1, 0):
+            m.set_search_path(path)
+            r = ix.search_batch(queries, threshold, limit)
+            assert len(r) == nq
+            got_counts = np.diff(r.offsets)
+            assert np.array_equal(got_counts, counts), (path, np.nonzero(got_counts != counts)[0][:10])
+            for q in range(nq):
+                n = int(counts[q])
+                kids, scores, _, _ = r.query(q)
+                assert np.array_equal(scores.view(np.uint32), sc[q, :n].view(np.uint32)), (path, q, scores[:8], sc[q, :8])
+                assert np.array_equal(kids, kid_of_ext[ext[q, :n]]), (path, q, kids[:8], kid_of_ext[ext[q, :8]])
+    finally:
+        m.set_search_path(0)
     return r
 
 
@@ -412,7 +421,17 @@ def test_properties_full_size(ssb):
         same = sc[:, :-1] == sc[:, 1:]
         assert np.all(kid[:, :-1][same] < kid[:, 1:][same])          # ties: kid ascending
         ms, msk, st = ix.search_resident(nq, 0.0, 100)
-        assert st["nFast"] == nq and st["nDense"] == 0 and st["nOverflow"] == 0
+        assert st["nFast"] == nq and st["nDense"] == 0 and st["nOverflow"] == 0 and st["nHash"] == 0
+        # the other fast kernel (k_hash_search first) must answer the batch identically, and answer most of it itself
+        try:
+            ssb.set_search_path(1)
+            r3 = ix.search_batch(q, 0.0, 100)
+            _, _, st3 = ix.search_resident(nq, 0.0, 100)
+        finally:
+            ssb.set_search_path(0)
+        assert np.array_equal(r1.offsets, r3.offsets) and np.array_equal(r1.kids, r3.kids)
+        assert np.array_equal(r1.scores.view(np.uint32), r3.scores.view(np.uint32))
+        assert st3["nHash"] + st3["nHashHandover"] == nq and st3["nHash"] > nq // 2 and st3["nDense"] == 0, st3
         exact = ix.search_batch(keys.slice(1000, 1064), 0.0, 5, strings=True)
         for i in range(64):
             assert exact.query(i)[3][0] == keys.get(1000 + i)
