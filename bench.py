@@ -145,8 +145,10 @@ def main():
     ap.add_argument("--cpu-queries", type=int, default=256, help="queries per step of the CPU reference leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-exchange", action="store_true", help="N>1: print CUDA-event times of the exchange phases (stderr)")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1: fused export/merge kernels storing into NVLink peer memory (default) or NCCL all-to-all + all-gather")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2p-barrier", "nccl"],
+                    help="N>1: p2p = export/merge kernels storing into NVLink peer memory with a device-side epoch hand-over, no "
+                         "collective at all (default); p2p-barrier = the same stores with two 4-byte all-reduces as barriers and "
+                         "the results replicated on every rank; nccl = NCCL all-to-all + all-gather")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -157,7 +159,8 @@ def main():
                f"threshold {args.threshold:g}, top-{args.limit}"
     config = {"workload": workload, "keys": args.keys, "batch": args.batch, "limit": args.limit, "threshold": args.threshold,
               "gSize": 3, "rowSize": 1,
-              "sharding": f"key-range x{world}; per-query top-k merge, exchange={args.exchange}" if world > 1 else "single shard",
+              "sharding": f"key-range x{world}; per-query top-k merge, exchange={args.exchange}; e2e: every rank returns the merged "
+                          f"results of its 1/{world} slice of the batch to its host" if world > 1 else "single shard",
               "l2": "inputs larger than L2: new query batch every step, ~184 KB of postings per query"}
 
     if args.impl == "reference":
@@ -226,7 +229,8 @@ def main():
     qptrs = [b.pointers() for b in batches]
     rec_bytes = RECORD_DTYPE.itemsize
     sliced = world > 1 and args.batch % world == 0
-    use_p2p = sliced and args.exchange == "p2p"
+    use_p2p = sliced and args.exchange in ("p2p", "p2p-barrier")
+    use_signal = sliced and args.exchange == "p2p"
     if world > 1:
         part_q = args.batch // world if sliced else 0
         host_rec = torch.empty((args.batch, args.limit, rec_bytes), dtype=torch.uint8, pin_memory=True)
@@ -235,14 +239,19 @@ def main():
     if use_p2p:
         # result / receive buffers are cudaMalloc'ed by the engine and opened in every peer process through CUDA IPC
         recv_ptr = api.device_alloc(world * part_q * args.limit * rec_bytes)
+        recv2_ptr = api.device_alloc(world * part_q * args.limit * rec_bytes)      # exchanges alternate between two receive buffers
+        flags_ptr = api.device_alloc(64)
+        api.device_memset(flags_ptr, 0, 64)
         merged_ptr = api.device_alloc(args.batch * args.limit * rec_bytes)
         counts_ptr = api.device_alloc(args.batch * 4)
         handles = [None] * world
-        dist.all_gather_object(handles, tuple(api.ipc_get_handle(p) for p in (recv_ptr, merged_ptr, counts_ptr)))
+        dist.all_gather_object(handles, tuple(api.ipc_get_handle(p) for p in (recv_ptr, merged_ptr, counts_ptr, recv2_ptr, flags_ptr)))
         try:
             peer_recv = [recv_ptr if r == rank else api.ipc_open_handle(handles[r][0]) for r in range(world)]
             peer_merged = [merged_ptr if r == rank else api.ipc_open_handle(handles[r][1]) for r in range(world)]
             peer_counts = [counts_ptr if r == rank else api.ipc_open_handle(handles[r][2]) for r in range(world)]
+            peer_recv2 = [recv2_ptr if r == rank else api.ipc_open_handle(handles[r][3]) for r in range(world)]
+            peer_flags = [flags_ptr if r == rank else api.ipc_open_handle(handles[r][4]) for r in range(world)]
             ok = torch.ones(1, device="cuda")
         except RuntimeError:
             ok = torch.zeros(1, device="cuda")
@@ -260,6 +269,7 @@ def main():
             gathered = torch.empty((world, args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
 
     xprof = []
+    epoch = [0]
     if world > 1:
         xev0, xev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -271,10 +281,20 @@ def main():
 
     def exchange():
         """per-query top-k merge across the key-range shards; every rank merges a 1/N slice of the queries.
-        p2p : the export kernel stores each record into the merging rank's buffer over NVLink, the merge kernel stores its
-              slice of final records into every rank's result buffer; the only collectives are two 4-byte all-reduces that
-              act as cross-rank barriers.
+        p2p : the export kernel stores each record into the merging rank's buffer over NVLink and then signals the exchange's
+              epoch into every rank's flags; the merge kernel waits for the flags of all shards and keeps its slice of final
+              records on its own rank. No collective, no host round trip between the two kernels.
+        p2p-barrier: the same stores, two 4-byte all-reduces as cross-rank barriers, merged slices stored into every rank.
         nccl: all-to-all of the records, merge kernel, all-gather of the merged slices."""
+        if use_signal:
+            epoch[0] += 1
+            e = epoch[0]
+            ix.export_records_p2p_signal(args.batch, args.limit, peer_recv2 if e & 1 else peer_recv, rank, peer_flags, e)
+            api.merge_records_p2p_wait(recv2_ptr if e & 1 else recv_ptr, world, part_q, args.limit, [merged_ptr], [counts_ptr], rank,
+                                       flags_ptr, e)
+            xev1.record()
+            torch.cuda.synchronize()
+            return
         if use_p2p:
             # everything below is enqueued on the default stream: kernel -> 4-byte all-reduce (cross-rank barrier: all
             # exports have landed) -> kernel -> all-reduce (all merged slices have landed); one host sync at the end
@@ -306,7 +326,18 @@ def main():
         torch.cuda.synchronize()
 
     def results_to_host():
-        if use_p2p:
+        """every rank delivers the merged results of the query slice it merged (one process per GPU: the caller of rank r gets
+        the answers to queries [r * B/N, (r+1) * B/N)); without slicing rank-local copies of the whole batch."""
+        if sliced:
+            q0 = rank * part_q
+            if use_p2p:
+                api.memcpy_d2h(host_rec.numpy()[q0:q0 + part_q], merged_ptr + q0 * args.limit * rec_bytes)
+                api.memcpy_d2h(host_cnt.numpy()[q0:q0 + part_q], counts_ptr + q0 * 4)
+            else:
+                host_rec[q0:q0 + part_q].copy_(part, non_blocking=True)
+                host_cnt[q0:q0 + part_q].copy_(pcount, non_blocking=True)
+                torch.cuda.synchronize()
+        elif use_p2p:
             api.memcpy_d2h(host_rec.numpy(), merged_ptr)
             api.memcpy_d2h(host_cnt.numpy(), counts_ptr)
         else:
@@ -338,7 +369,7 @@ def main():
             ix.search_batch_device(qptrs[s], args.batch, args.threshold, args.limit)
             exchange()
             results_to_host()
-            n_results = int(host_cnt.sum().item())
+            n_results = int(host_cnt[rank * part_q:(rank + 1) * part_q].sum().item()) if sliced else int(host_cnt.sum().item())
         t1 = time.perf_counter()
         # (2) device part only, the same batch resident in HBM
         barrier()

@@ -96,6 +96,18 @@ int ssb_ipc_close_handle(void* d_ptr);
 int ssb_export_records_p2p(ssb_index* ix, uint32_t nq, uint32_t limit, void* const* peerRecv, uint32_t nRanks, uint32_t myRank);
 int ssb_merge_records_p2p(const void* d_recv, uint32_t nShards, uint32_t nqLocal, uint32_t limit, void* const* peerMerged,
                           void* const* peerCounts, uint32_t nRanks, uint32_t myRank);
+/* The same pair with a device-side hand-over instead of the barrier between them (no collective at all): every rank owns
+ * an array of N u32 flags (ssb_device_alloc + ssb_device_memset(.., 0, ..), opened by the peers). The export kernel stores
+ * `epoch` into peerFlags[j][myRank] on every rank j once all its records have landed (system-scope release); the merge
+ * kernel waits until d_myFlags[0..nShards) have all reached `epoch` (acquire). Epochs start at 1 and grow by one per
+ * exchange; consecutive exchanges must alternate between two sets of receive buffers (a rank can be one exchange ahead of a
+ * peer). nOut = number of result buffers the merge stores into (1 with the rank's own buffers: every rank keeps only the
+ * slice it merged; N to replicate the results everywhere — then a barrier is needed before reading the other slices). */
+int ssb_export_records_p2p_signal(ssb_index* ix, uint32_t nq, uint32_t limit, void* const* peerRecv, uint32_t nRanks, uint32_t myRank,
+                                  void* const* peerFlags, uint32_t epoch);
+int ssb_merge_records_p2p_wait(const void* d_recv, uint32_t nShards, uint32_t nqLocal, uint32_t limit, void* const* peerMerged,
+                               void* const* peerCounts, uint32_t nOut, uint32_t myRank, const void* d_myFlags, uint32_t epoch);
+int ssb_device_memset(void* d_ptr, int value, uint64_t bytes);
 
 #ifdef __cplusplus
 }

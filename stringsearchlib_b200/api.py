@@ -73,6 +73,10 @@ def core_library():
     lib.ssb_ipc_close_handle.argtypes = [c_void_p]
     lib.ssb_export_records_p2p.argtypes = [c_void_p, c_uint32, c_uint32, POINTER(c_void_p), c_uint32, c_uint32]
     lib.ssb_merge_records_p2p.argtypes = [c_void_p, c_uint32, c_uint32, c_uint32, POINTER(c_void_p), POINTER(c_void_p), c_uint32, c_uint32]
+    lib.ssb_export_records_p2p_signal.argtypes = [c_void_p, c_uint32, c_uint32, POINTER(c_void_p), c_uint32, c_uint32, POINTER(c_void_p), c_uint32]
+    lib.ssb_merge_records_p2p_wait.argtypes = [c_void_p, c_uint32, c_uint32, c_uint32, POINTER(c_void_p), POINTER(c_void_p), c_uint32, c_uint32,
+                                               c_void_p, c_uint32]
+    lib.ssb_device_memset.argtypes = [c_void_p, c_int, c_uint64]
     lib._ssb_typed = True
     return lib
 
@@ -309,6 +313,11 @@ class Index:
         """fused export + exchange: query q's records go straight into peer_recv[q // (nq/N)] (peer-mapped pointers)."""
         _check(self._lib.ssb_export_records_p2p(self._h, nq, limit, _ptr_list(peer_recv), len(peer_recv), rank))
 
+    def export_records_p2p_signal(self, nq, limit, peer_recv, rank, peer_flags, epoch):
+        """export_records_p2p + device-side signal: peer_flags[j][rank] = epoch once the records have landed on every rank."""
+        _check(self._lib.ssb_export_records_p2p_signal(self._h, nq, limit, _ptr_list(peer_recv), len(peer_recv), rank,
+                                                       _ptr_list(peer_flags), epoch))
+
     def export_records(self, nq, limit, device_ptr):
         if self._lib.ssb_export_records(self._h, nq, limit, device_ptr) != 0:
             raise RuntimeError(self._lib.ssb_last_error().decode())
@@ -356,6 +365,17 @@ def merge_records_p2p(recv_ptr, n_shards, nq_local, limit, peer_merged, peer_cou
     """merges this rank's slice of queries and stores the result into every rank's buffers (peer-mapped pointers)."""
     _check(core_library().ssb_merge_records_p2p(recv_ptr, n_shards, nq_local, limit, _ptr_list(peer_merged), _ptr_list(peer_counts),
                                                 len(peer_merged), rank))
+
+
+def merge_records_p2p_wait(recv_ptr, n_shards, nq_local, limit, out_merged, out_counts, rank, my_flags, epoch):
+    """like merge_records_p2p, but the kernel itself waits for the peers' export kernels (flags >= epoch); out_merged /
+    out_counts: the result buffers to store into (usually just this rank's own)."""
+    _check(core_library().ssb_merge_records_p2p_wait(recv_ptr, n_shards, nq_local, limit, _ptr_list(out_merged), _ptr_list(out_counts),
+                                                     len(out_merged), rank, my_flags, epoch))
+
+
+def device_memset(ptr, value, nbytes):
+    _check(core_library().ssb_device_memset(ptr, int(value), int(nbytes)))
 
 
 def merge_records(gathered_ptr, n_shards, nq, limit, merged_ptr, counts_ptr):

@@ -590,6 +590,33 @@ SSB_API int ssb_export_records_p2p(ssb_index* ix, uint32_t nq, uint32_t limit, v
 		return 0;
 	}, -1);
 }
+SSB_API int ssb_export_records_p2p_signal(ssb_index* ix, uint32_t nq, uint32_t limit, void* const* peerRecv, uint32_t nRanks, uint32_t myRank,
+                                          void* const* peerFlags, uint32_t epoch)
+{
+	if (!ix || !peerFlags) return -1;
+	return guarded([&] {
+		g_engine.init();
+		std::lock_guard<std::mutex> lk(ix->mu);
+		export_records_p2p(ix->dix, ix->ws, nq, limit, reinterpret_cast<MergeRecord* const*>(peerRecv), nRanks, myRank, 0,
+		                   reinterpret_cast<uint32_t* const*>(peerFlags), epoch);
+		return 0;
+	}, -1);
+}
+SSB_API int ssb_merge_records_p2p_wait(const void* d_recv, uint32_t nShards, uint32_t nqLocal, uint32_t limit, void* const* peerMerged,
+                                       void* const* peerCounts, uint32_t nOut, uint32_t myRank, const void* d_myFlags, uint32_t epoch)
+{
+	if (!d_myFlags) return -1;
+	return guarded([&] {
+		g_engine.init();
+		merge_records_p2p(static_cast<const MergeRecord*>(d_recv), nShards, nqLocal, limit, reinterpret_cast<MergeRecord* const*>(peerMerged),
+		                  reinterpret_cast<uint32_t* const*>(peerCounts), nOut, myRank, 0, static_cast<const uint32_t*>(d_myFlags), epoch);
+		return 0;
+	}, -1);
+}
+SSB_API int ssb_device_memset(void* d_ptr, int value, uint64_t bytes)
+{
+	return guarded([&] { g_engine.init(); SSB_CUDA(cudaMemset(d_ptr, value, bytes)); return 0; }, -1);
+}
 SSB_API int ssb_merge_records_p2p(const void* d_recv, uint32_t nShards, uint32_t nqLocal, uint32_t limit, void* const* peerMerged,
                                   void* const* peerCounts, uint32_t nRanks, uint32_t myRank)
 {

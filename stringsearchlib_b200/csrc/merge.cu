@@ -43,19 +43,48 @@ __global__ void k_export_records(const uint32_t* __restrict__ outCount, const ui
 
 struct PeerPtrs { MergeRecord* p[16]; };
 struct PeerCounts { uint32_t* p[16]; };
+struct PeerFlags { uint32_t* p[16]; };        // flags[j][i] on rank j: last epoch whose records rank i has delivered
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // fused export + exchange: the record of query q goes straight into the receive buffer of the rank that merges q
 // (peer-mapped memory, plain 8-byte stores over NVLink): recv[j] is laid out [shard][nq/N][limit].
 __global__ void k_export_records_p2p(const uint32_t* __restrict__ outCount, const uint32_t* __restrict__ outKid,
                                      const float* __restrict__ outScore, uint32_t stride, uint32_t nq, uint32_t limit,
                                      const uint32_t* __restrict__ keyOff, const uint64_t* __restrict__ keyRow,
-                                     const uint64_t* __restrict__ keyHash, PeerPtrs peers, uint32_t nRanks, uint32_t myRank)
+                                     const uint64_t* __restrict__ keyHash, PeerPtrs peers, uint32_t nRanks, uint32_t myRank,
+                                     uint32_t* __restrict__ done, PeerFlags flags, uint32_t epoch)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= (uint64_t)nq * limit) return;
-	const uint32_t q = (uint32_t)(i / limit), r = (uint32_t)(i % limit);
-	const uint32_t part = nq / nRanks, j = q / part, ql = q - j * part;
-	peers.p[j][((size_t)myRank * part + ql) * limit + r] = make_record(q, r, outCount, outKid, outScore, stride, keyOff, keyRow, keyHash);
+	if (i < (uint64_t)nq * limit) {
+		const uint32_t q = (uint32_t)(i / limit), r = (uint32_t)(i % limit);
+		const uint32_t part = nq / nRanks, j = q / part, ql = q - j * part;
+		peers.p[j][((size_t)myRank * part + ql) * limit + r] = make_record(q, r, outCount, outKid, outScore, stride, keyOff, keyRow, keyHash);
+	}
+	if (!done) return;
+	// device-side signal instead of a collective: the last CTA to finish tells every peer "epoch delivered". The fence of
+	// thread 0 is cumulative over the CTA's stores (ordered before it by the barrier); the release stores publish them.
+	__shared__ uint32_t sLast;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence_system();
+		sLast = atomicAdd(done, 1u) == gridDim.x - 1;
+	}
+	__syncthreads();
+	if (sLast) {
+		if (threadIdx.x == 0) *done = 0;
+		__threadfence_system();
+		if (threadIdx.x < nRanks) st_release_sys(flags.p[threadIdx.x] + myRank, epoch);
+	}
 }
 
 __device__ __forceinline__ bool rec_less(uint64_t a1, uint64_t b1, uint64_t a2, uint64_t b2) { return a1 != a2 ? a1 < a2 : b1 < b2; }
@@ -63,8 +92,18 @@ __device__ __forceinline__ bool rec_less(uint64_t a1, uint64_t b1, uint64_t a2, 
 // one CTA per query. Shared memory: A (order key hi: ~score | length), B (row), H (hash) of p slots, hash table of 2p u32.
 __global__ void k_merge_records(const MergeRecord* __restrict__ gathered, uint32_t nShards, uint32_t nq, uint32_t limit, uint32_t runLen,
                                 uint32_t p, MergeRecord* __restrict__ merged, uint32_t* __restrict__ counts, PeerPtrs outPeers,
-                                uint32_t nOutPeers, uint32_t outQueryBase, PeerCounts outCountsPeers)
+                                uint32_t nOutPeers, uint32_t outQueryBase, PeerCounts outCountsPeers, const uint32_t* __restrict__ waitFlags,
+                                uint32_t epoch)
 {
+	if (waitFlags) {
+		// the runs come straight from the peers' export kernels: wait until every shard has signalled this epoch
+		if (threadIdx.x < nShards) {
+			uint32_t spins = 0;
+			while ((int32_t)(ld_acquire_sys(waitFlags + threadIdx.x) - epoch) < 0)
+				if (++spins > (1u << 28)) __trap();              // a peer that never delivers must not hang this GPU
+		}
+		__syncthreads();
+	}
 	extern __shared__ __align__(16) unsigned char mg_smem[];
 	uint64_t* A = reinterpret_cast<uint64_t*>(mg_smem);
 	uint64_t* B = A + p;
@@ -206,7 +245,7 @@ void export_records(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, uin
 }
 
 void export_records_p2p(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, uint32_t limit, MergeRecord* const* peerRecv,
-                        uint32_t nRanks, uint32_t myRank, cudaStream_t s)
+                        uint32_t nRanks, uint32_t myRank, cudaStream_t s, uint32_t* const* peerFlags, uint32_t epoch)
 {
 	if (limit == 0 || limit > FAST_KLIM) throw std::runtime_error("export_records_p2p: limit must be in [1, FAST_KLIM]");
 	if (nq > ws.capQ || nRanks == 0 || nRanks > 16 || nq % nRanks) throw std::runtime_error("export_records_p2p: bad geometry");
@@ -214,8 +253,16 @@ void export_records_p2p(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq,
 	PeerPtrs pp{};
 	for (uint32_t i = 0; i < nRanks; ++i) pp.p[i] = peerRecv[i];
 	const uint64_t n = (uint64_t)nq * limit;
+	PeerFlags pf{};
+	uint32_t* done = nullptr;
+	if (peerFlags) {
+		for (uint32_t i = 0; i < nRanks; ++i) pf.p[i] = peerFlags[i];
+		if (!ws.exportDone.get()) { ws.exportDone.alloc(1, s); ws.exportDone.zero(s); }
+		done = ws.exportDone.get();
+	}
 	k_export_records_p2p<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.outCount.get(), ws.outKid.get(), ws.outScore.get(), limit, nq, limit,
-	                                                                 ix.keyOff.get(), ix.keyRow.get(), ix.keyHash.get(), pp, nRanks, myRank);
+	                                                                 ix.keyOff.get(), ix.keyRow.get(), ix.keyHash.get(), pp, nRanks, myRank,
+	                                                                 done, pf, epoch);
 	SSB_LAUNCH_CHECK();
 }
 
@@ -223,9 +270,11 @@ void export_records_p2p(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq,
 // groups first (top-limit of a union is contained in the union of the groups' top-limits; best-entry dedupe is associative)
 constexpr uint32_t MERGE_MAX_SLOTS = 4096;
 static void merge_impl(const MergeRecord* d_gathered, uint32_t nShards, uint32_t nq, uint32_t limit, MergeRecord* d_out, uint32_t* d_outCount,
-                       const PeerPtrs* peers, const PeerCounts* peerCounts, uint32_t nRanks, uint32_t myRank, cudaStream_t s)
+                       const PeerPtrs* peers, const PeerCounts* peerCounts, uint32_t nRanks, uint32_t myRank, cudaStream_t s,
+                       const uint32_t* waitFlags = nullptr, uint32_t epoch = 0)
 {
 	MergeGeom g = merge_geometry(nShards, limit);
+	bool grouped = false;                       // the group merges have waited for the peers already
 	DevBuf<MergeRecord> tmp;
 	DevBuf<uint32_t> tmpCount;
 	while (g.p > MERGE_MAX_SLOTS && nShards > 2) {
@@ -239,10 +288,12 @@ static void merge_impl(const MergeRecord* d_gathered, uint32_t nShards, uint32_t
 			const uint32_t first = gi * group, cnt = std::min(group, nShards - first);
 			PeerPtrs none{}; PeerCounts nonec{};
 			k_merge_records<<<nq, gg.threads, gg.smem, s>>>(d_gathered + (size_t)first * nq * limit, cnt, nq, limit, gg.runLen, gg.p,
-			                                              next.get() + (size_t)gi * nq * limit, tmpCount.get(), none, 0, 0, nonec);
+			                                              next.get() + (size_t)gi * nq * limit, tmpCount.get(), none, 0, 0, nonec,
+			                                              waitFlags ? waitFlags + first : nullptr, epoch);
 			SSB_LAUNCH_CHECK();
 		}
 		tmp = std::move(next);
+		grouped = true;
 		d_gathered = tmp.get();
 		nShards = nGroups;
 		g = merge_geometry(nShards, limit);
@@ -251,7 +302,7 @@ static void merge_impl(const MergeRecord* d_gathered, uint32_t nShards, uint32_t
 	PeerPtrs pp{}; PeerCounts pc{};
 	if (peers) { pp = *peers; pc = *peerCounts; }
 	k_merge_records<<<nq, g.threads, g.smem, s>>>(d_gathered, nShards, nq, limit, g.runLen, g.p, d_out, d_outCount, pp, peers ? nRanks : 0,
-	                                              peers ? myRank * nq : 0, pc);
+	                                              peers ? myRank * nq : 0, pc, grouped ? nullptr : waitFlags, epoch);
 	SSB_LAUNCH_CHECK();
 }
 
@@ -262,12 +313,12 @@ void merge_records(const MergeRecord* d_gathered, uint32_t nShards, uint32_t nq,
 }
 
 void merge_records_p2p(const MergeRecord* d_recv, uint32_t nShards, uint32_t nqLocal, uint32_t limit, MergeRecord* const* peerMerged,
-                       uint32_t* const* peerCounts, uint32_t nRanks, uint32_t myRank, cudaStream_t s)
+                       uint32_t* const* peerCounts, uint32_t nRanks, uint32_t myRank, cudaStream_t s, const uint32_t* waitFlags, uint32_t epoch)
 {
-	if (nRanks == 0 || nRanks > 16) throw std::runtime_error("merge_records_p2p: bad geometry");
+	if (nRanks == 0 || nRanks > 16 || (waitFlags && nShards > 16)) throw std::runtime_error("merge_records_p2p: bad geometry");
 	PeerPtrs pp{}; PeerCounts pc{};
 	for (uint32_t i = 0; i < nRanks; ++i) { pp.p[i] = peerMerged[i]; pc.p[i] = peerCounts[i]; }
-	merge_impl(d_recv, nShards, nqLocal, limit, nullptr, nullptr, &pp, &pc, nRanks, myRank, s);
+	merge_impl(d_recv, nShards, nqLocal, limit, nullptr, nullptr, &pp, &pc, nRanks, myRank, s, waitFlags, epoch);
 }
 
 }   // namespace ssb

@@ -59,6 +59,7 @@ struct SearchWorkspace {
 	DevBuf<uint64_t> csrRow, csrStr;
 	// dense scratch
 	DevBuf<uint32_t> cnt, entry;
+	DevBuf<uint32_t> exportDone;            // CTA counter of the signalling export kernel
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
 	uint32_t capQ = 0, stride = 0;
 	size_t capChars = 0;
@@ -110,9 +111,13 @@ void merge_records(const MergeRecord* d_gathered, uint32_t nShards, uint32_t nq,
                    cudaStream_t s);
 // fused variants over peer-mapped memory (NVLink P2P stores): export writes query q's records into the receive buffer of
 // the rank that merges q ([shard][nq/N][limit]); merge writes its slice of final records/counts into every rank's buffers.
+// peerFlags / waitFlags (optional): device-side hand-over instead of a collective between the two calls — the export kernel
+// stores `epoch` into flags[myRank] on every peer once its records have landed, the merge kernel waits until its own flags
+// of all shards have reached `epoch` (epochs grow by one per exchange; receive buffers alternate between two sets).
 void export_records_p2p(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, uint32_t limit, MergeRecord* const* peerRecv,
-                        uint32_t nRanks, uint32_t myRank, cudaStream_t s);
+                        uint32_t nRanks, uint32_t myRank, cudaStream_t s, uint32_t* const* peerFlags = nullptr, uint32_t epoch = 0);
 void merge_records_p2p(const MergeRecord* d_recv, uint32_t nShards, uint32_t nqLocal, uint32_t limit, MergeRecord* const* peerMerged,
-                       uint32_t* const* peerCounts, uint32_t nRanks, uint32_t myRank, cudaStream_t s);
+                       uint32_t* const* peerCounts, uint32_t nRanks, uint32_t myRank, cudaStream_t s, const uint32_t* waitFlags = nullptr,
+                       uint32_t epoch = 0);
 
 }   // namespace ssb

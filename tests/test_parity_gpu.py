@@ -361,6 +361,56 @@ def test_key_range_shards_p2p_exchange(ssb, oracle_built):
         api.device_free(p)
 
 
+def test_key_range_shards_p2p_signal_wait(ssb, oracle_built):
+    """the exchange without any collective: the export kernel signals an epoch into every rank's flags, the merge kernel
+    waits for the flags of all shards; two exchanges on alternating receive buffers, every rank keeps only the slice it
+    merged. N emulated ranks on one GPU (all buffers local, the indexing is the multi-GPU one)."""
+    import torch
+    from stringsearchlib_b200 import synth
+    from stringsearchlib_b200 import api
+    n, nq, limit, N = 40000, 128, 20, 4
+    keys = synth.ascii_keys(n)
+    S = oracle_built.SpecIndex(keys, 1)
+    o = S.tables()
+    rb = api.RECORD_DTYPE.itemsize
+    part = nq // N
+    recv = [[api.device_alloc(N * part * limit * rb) for _ in range(N)] for _ in range(2)]
+    merged = [api.device_alloc(nq * limit * rb) for _ in range(N)]
+    cnts = [api.device_alloc(nq * 4) for _ in range(N)]
+    flags = [api.device_alloc(64) for _ in range(N)]
+    for f in flags:
+        api.device_memset(f, 0, 64)
+    bounds = np.linspace(0, n, N + 1).astype(int)
+    shards = [ssb.Index(keys.slice(bounds[r], bounds[r + 1]), 1, row_base=int(bounds[r])) for r in range(N)]
+    for epoch in (1, 2):
+        q = synth.queries_from(keys, nq, stride=epoch)
+        counts, ext, sc = S.search_batch(q, 0.0, limit)
+        for r in range(N):
+            shards[r].search_batch(q, 0.0, limit)
+            shards[r].export_records_p2p_signal(nq, limit, recv[epoch & 1], r, flags, epoch)
+        for r in range(N):
+            api.merge_records_p2p_wait(recv[epoch & 1][r], N, part, limit, [merged[r]], [cnts[r]], r, flags[r], epoch)
+        torch.cuda.synchronize()
+        for r in range(N):
+            fl = np.zeros(16, np.uint32)
+            api.memcpy_d2h(fl, flags[r])
+            assert np.all(fl[:N] == epoch)
+            rec = np.zeros((nq, limit), api.RECORD_DTYPE)
+            mc = np.zeros(nq, np.uint32)
+            api.memcpy_d2h(rec, merged[r])
+            api.memcpy_d2h(mc, cnts[r])
+            sl = slice(r * part, (r + 1) * part)
+            assert np.array_equal(mc[sl], counts[sl])
+            for i in range(r * part, (r + 1) * part):
+                c = int(counts[i])
+                assert np.array_equal(rec["scoreBits"][i, :c], sc[i, :c].view(np.uint32))
+                assert np.array_equal(rec["row"][i, :c], o["firstRowExt"][ext[i, :c]])
+    for ix in shards:
+        ix.close()
+    for p in recv[0] + recv[1] + merged + cnts + flags:
+        api.device_free(p)
+
+
 def test_merge_collapses_duplicates_and_large_limit(ssb, oracle_built):
     """the same key strings in several shards collapse to one entry (best score); 8 shards x limit 1000 exercises the
     hierarchical merge (more records than one CTA's shared memory holds)."""
