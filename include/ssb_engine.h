@@ -30,6 +30,12 @@ ssb_index* ssb_index_create(const void* const* words, uint64_t size, uint16_t ro
 ssb_index* ssb_index_create_packed(const void* units, const uint64_t* offsets, const uint8_t* isNull, uint64_t size,
                                    uint16_t rowSize, const float* weight, uint16_t gSize, int wide, uint64_t rowBase);
 void ssb_index_destroy(ssb_index* ix);
+/* ---- serialisation (build once, search many; the reference has no equivalent and re-indexes from words[]).
+ * ssb_index_save writes every table of the index (device arrays + host key table + validChar) to `path`; ssb_index_load
+ * returns an index that answers exactly like the saved one (same ids, same ranked lists), on the current device. The file
+ * format is private to one engine version (magic + version are checked). 0 / non-NULL on success. */
+int ssb_index_save(ssb_index* ix, const char* path);
+ssb_index* ssb_index_load(const char* path);
 uint64_t ssb_index_size(const ssb_index* ix);      /* getSize    (nGramSearch.hpp:488) */
 uint64_t ssb_index_lib_size(const ssb_index* ix);  /* getLibSize (nGramSearch.hpp:496) */
 void ssb_index_set_valid_char(ssb_index* ix, const char* chars, int n);   /* dllmain.cpp:142 */

@@ -77,6 +77,9 @@ def core_library():
     lib.ssb_merge_records_p2p_wait.argtypes = [c_void_p, c_uint32, c_uint32, c_uint32, POINTER(c_void_p), POINTER(c_void_p), c_uint32, c_uint32,
                                                c_void_p, c_uint32]
     lib.ssb_device_memset.argtypes = [c_void_p, c_int, c_uint64]
+    lib.ssb_index_save.argtypes = [c_void_p, c_char_p]
+    lib.ssb_index_load.argtypes = [c_char_p]
+    lib.ssb_index_load.restype = c_void_p
     lib._ssb_typed = True
     return lib
 
@@ -162,6 +165,22 @@ class Index:
         self._h = self._lib.ssb_index_create(ptrs, n, row_size, wp, g_size, int(wide), row_base)
         if not self._h:
             raise RuntimeError("ssb_index_create failed: " + self._lib.ssb_last_error().decode())
+        return self
+
+    def save(self, path):
+        """writes every table of the index to `path` (ssb_index_save)."""
+        if self._lib.ssb_index_save(self._h, os.fsencode(path)) != 0:
+            raise RuntimeError(self._lib.ssb_last_error().decode())
+
+    @classmethod
+    def load(cls, path):
+        """an index that answers exactly like the one saved to `path` (ssb_index_load)."""
+        self = cls.__new__(cls)
+        self._lib = core_library()
+        self._h = self._lib.ssb_index_load(os.fsencode(path))
+        if not self._h:
+            raise RuntimeError("ssb_index_load failed: " + self._lib.ssb_last_error().decode())
+        self.wide = self.info()["unit"] == 4
         return self
 
     def close(self):

@@ -28,6 +28,10 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 // every kernel launch of the engine goes through SSB_LAUNCH_CHECK(): it validates the launch and counts it
 // (ssb_kernel_launches() feeds bench.py's "gpu_launches")
 inline std::atomic<uint64_t> g_kernel_launches{0};
+// set by an atexit handler registered at engine start-up, i.e. BEFORE the static destructors of this library run: objects
+// that are still alive then (cached staging buffers, indexes a host never disposed of) must not call into a CUDA runtime
+// that is tearing down — the process is about to return everything to the OS anyway
+inline std::atomic<bool> g_exiting{false};
 // which kernel answers the fast queries first: 0 = k_fast_search (register K-way merge), 1 = k_hash_search (duplicate detection
 // by hashing; hands what it cannot take to k_fast_search). Both are exact; see DESIGN.md for why the merge is the default.
 inline std::atomic<int> g_search_path{-1};       // -1: not set -> environment SSB_HASH=1 selects 1, else 0
@@ -56,7 +60,7 @@ public:
 	void reserve(size_t n, cudaStream_t s = 0) { if (n > n_) alloc(n + n / 4, s); }
 	void release()
 	{
-		if (p_) cudaFreeAsync(p_, stream_);
+		if (p_ && !g_exiting.load(std::memory_order_relaxed)) cudaFreeAsync(p_, stream_);
 		p_ = nullptr; n_ = 0;
 	}
 	void zero(cudaStream_t s) { if (n_) SSB_CUDA(cudaMemsetAsync(p_, 0, n_ * sizeof(T), s)); }
@@ -77,7 +81,7 @@ public:
 	PinBuf() = default;
 	PinBuf(const PinBuf&) = delete;
 	PinBuf& operator=(const PinBuf&) = delete;
-	~PinBuf() { if (p_) cudaFreeHost(p_); }
+	~PinBuf() { if (p_ && !g_exiting.load(std::memory_order_relaxed)) cudaFreeHost(p_); }
 	void reserve(size_t n)
 	{
 		if (n <= n_) return;

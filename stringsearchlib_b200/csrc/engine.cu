@@ -31,6 +31,7 @@ struct EngineGlobals {
 			SSB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
 			uint64_t keep = ~0ull;   // keep freed blocks cached in the pool: no OS round trips between batches
 			SSB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+			std::atexit([] { g_exiting.store(true); });
 		});
 		SSB_CUDA(cudaSetDevice(device));
 	}
@@ -86,7 +87,7 @@ struct SlabPool {
 	std::vector<Slab*> free;
 	~SlabPool()
 	{
-		for (Slab* s : free) { cudaFreeHost(s->base); delete s; }
+		for (Slab* s : free) { if (!g_exiting.load()) cudaFreeHost(s->base); delete s; }
 	}
 	static size_t al(size_t x) { return (x + 63) & ~size_t(63); }
 	Slab* get(size_t capQ, size_t capResults)
@@ -141,7 +142,7 @@ struct ssb_index {
 	SearchStats lastStats;
 	~ssb_index()
 	{
-		if (stream) { cudaStreamSynchronize(stream); }
+		if (stream && !g_exiting.load()) { cudaStreamSynchronize(stream); }
 		// device buffers are released by their destructors (stream-ordered); the stream itself is destroyed last
 	}
 };
@@ -324,6 +325,67 @@ template <class F> auto guarded(F f, decltype(f()) fail) -> decltype(f())
 
 }   // namespace
 
+// ---- serialisation (no reference equivalent: the reference rebuilds its hash containers from words[] every time).
+// File = header (sizes, flags, validChar) + every device array as (u64 element count, raw bytes) + the host key table.
+namespace {
+struct IndexFileHeader {
+	char magic[8];
+	uint32_t version, headerBytes;
+	int32_t g, unit, symBits;
+	uint32_t indexed, K, T, E, G, P, nShort, maxTermLen, maxKeyLen, termUnits, keyUnits, A;
+	uint32_t identity, uniformW, multiEdgeKeys, packed;
+	float wmax;
+	uint64_t rowBase, hostKeyBytes;
+	uint8_t validLut[256];
+};
+constexpr char INDEX_MAGIC[8] = {'S', 'S', 'B', 'I', 'D', 'X', '1', 0};
+
+struct FileCloser { void operator()(FILE* f) const { if (f) fclose(f); } };
+using FilePtr = std::unique_ptr<FILE, FileCloser>;
+
+void write_all(FILE* f, const void* p, size_t n) { if (n && fwrite(p, 1, n, f) != n) throw std::runtime_error("ssb_index_save: write failed"); }
+void read_all(FILE* f, void* p, size_t n) { if (n && fread(p, 1, n, f) != n) throw std::runtime_error("ssb_index_load: truncated file"); }
+
+// device array <-> file through a pinned bounce buffer
+template <class T> void save_buf(FILE* f, const DevBuf<T>& b, size_t count, PinBuf<uint8_t>& bounce, cudaStream_t s)
+{
+	const uint64_t n = b.get() ? count : 0;
+	write_all(f, &n, 8);
+	const size_t chunk = bounce.size();
+	for (size_t off = 0; off < n * sizeof(T); off += chunk) {
+		const size_t len = std::min(chunk, n * sizeof(T) - off);
+		SSB_CUDA(cudaMemcpyAsync(bounce.get(), reinterpret_cast<const uint8_t*>(b.get()) + off, len, cudaMemcpyDeviceToHost, s));
+		SSB_CUDA(cudaStreamSynchronize(s));
+		write_all(f, bounce.get(), len);
+	}
+}
+template <class T> void load_buf(FILE* f, DevBuf<T>& b, PinBuf<uint8_t>& bounce, cudaStream_t s)
+{
+	uint64_t n = 0;
+	read_all(f, &n, 8);
+	if (n > (1ull << 36)) throw std::runtime_error("ssb_index_load: corrupt array size");
+	b.alloc(n, s);
+	const size_t chunk = bounce.size();
+	for (size_t off = 0; off < n * sizeof(T); off += chunk) {
+		const size_t len = std::min(chunk, n * sizeof(T) - off);
+		read_all(f, bounce.get(), len);
+		SSB_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(b.get()) + off, bounce.get(), len, cudaMemcpyHostToDevice, s));
+		SSB_CUDA(cudaStreamSynchronize(s));
+	}
+}
+// one visitor keeps the order of the arrays identical for save and load
+template <class F> void for_each_array(DeviceIndex& d, F f)
+{
+	f(d.symTable, d.symTable.size()); f(d.validLut, d.validLut.size());
+	f(d.gramCodes, (size_t)d.G); f(d.gramOff, (size_t)d.G + 1); f(d.postings, d.postings.size());
+	f(d.termOff, (size_t)d.T + 1); f(d.termChars, d.termChars.size()); f(d.termEdgeOff, (size_t)d.T + 1);
+	f(d.edgeKid, (size_t)d.E); f(d.edgeW, (size_t)d.E); f(d.shortTerms, (size_t)d.nShort);
+	f(d.keyOff, (size_t)d.K + 1); f(d.keyChars, d.keyChars.size()); f(d.keyEdgeOff, (size_t)d.K + 1);
+	f(d.keyEdgeTerm, (size_t)d.E); f(d.keyEdgeW, (size_t)d.E); f(d.keyWmax, (size_t)d.K); f(d.keyRow, (size_t)d.K);
+	f(d.keyHash, (size_t)d.K);
+}
+}   // namespace
+
 extern "C" {
 
 #define SSB_API __attribute__((visibility("default")))
@@ -355,13 +417,78 @@ SSB_API ssb_index* ssb_index_create_packed(const void* units, const uint64_t* of
 	return guarded([&]() -> ssb_index* { return create_from_packed(units, offsets, isNull, size, rowSize, weight, gSize, wide ? 4 : 1, rowBase); },
 	               nullptr);
 }
+SSB_API int ssb_index_save(ssb_index* ix, const char* path)
+{
+	if (!ix || !path) return -1;
+	return guarded([&] {
+		g_engine.init();
+		std::lock_guard<std::mutex> lk(ix->mu);
+		DeviceIndex& d = ix->dix;
+		FilePtr f(fopen(path, "wb"));
+		if (!f) throw std::runtime_error(std::string("ssb_index_save: cannot open ") + path);
+		IndexFileHeader h{};
+		memcpy(h.magic, INDEX_MAGIC, 8);
+		h.version = 1; h.headerBytes = sizeof(IndexFileHeader);
+		h.g = d.g; h.unit = d.unit; h.symBits = d.symBits;
+		h.indexed = d.indexed; h.K = d.K; h.T = d.T; h.E = d.E; h.G = d.G; h.P = d.P; h.nShort = d.nShort;
+		h.maxTermLen = d.maxTermLen; h.maxKeyLen = d.maxKeyLen; h.termUnits = d.termUnits; h.keyUnits = d.keyUnits; h.A = d.A;
+		h.identity = d.identity; h.uniformW = d.uniformW; h.multiEdgeKeys = d.multiEdgeKeys; h.packed = d.packed;
+		h.wmax = d.wmax; h.rowBase = d.rowBase; h.hostKeyBytes = ix->hk.charBytes;
+		memcpy(h.validLut, ix->validLut, 256);
+		write_all(f.get(), &h, sizeof(h));
+		PinBuf<uint8_t> bounce;
+		bounce.alloc_exact(16u << 20);
+		for_each_array(d, [&](auto& b, size_t count) { save_buf(f.get(), b, count, bounce, ix->stream); });
+		write_all(f.get(), ix->hk.chars, ix->hk.charBytes);
+		if (fflush(f.get()) != 0) throw std::runtime_error("ssb_index_save: flush failed");
+		return 0;
+	}, -1);
+}
+
+SSB_API ssb_index* ssb_index_load(const char* path)
+{
+	if (!path) return nullptr;
+	return guarded([&]() -> ssb_index* {
+		g_engine.init();
+		FilePtr f(fopen(path, "rb"));
+		if (!f) throw std::runtime_error(std::string("ssb_index_load: cannot open ") + path);
+		IndexFileHeader h{};
+		read_all(f.get(), &h, sizeof(h));
+		if (memcmp(h.magic, INDEX_MAGIC, 8) != 0 || h.version != 1 || h.headerBytes != sizeof(IndexFileHeader))
+			throw std::runtime_error("ssb_index_load: not an index file of this engine version");
+		if ((h.unit != 1 && h.unit != 4) || h.g < 1 || h.g > MAX_GSIZE) throw std::runtime_error("ssb_index_load: corrupt header");
+		auto ix = std::make_unique<ssb_index>();
+		SSB_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+		DeviceIndex& d = ix->dix;
+		d.g = h.g; d.unit = h.unit; d.symBits = h.symBits; d.indexed = h.indexed != 0;
+		d.K = h.K; d.T = h.T; d.E = h.E; d.G = h.G; d.P = h.P; d.nShort = h.nShort;
+		d.maxTermLen = h.maxTermLen; d.maxKeyLen = h.maxKeyLen; d.termUnits = h.termUnits; d.keyUnits = h.keyUnits; d.A = h.A;
+		d.identity = h.identity != 0; d.uniformW = h.uniformW != 0; d.multiEdgeKeys = h.multiEdgeKeys != 0; d.packed = h.packed != 0;
+		d.wmax = h.wmax; d.rowBase = h.rowBase;
+		memcpy(ix->validLut, h.validLut, 256);
+		PinBuf<uint8_t> bounce;
+		bounce.alloc_exact(16u << 20);
+		for_each_array(d, [&](auto& b, size_t) { load_buf(f.get(), b, bounce, ix->stream); });
+		ix->hk.reset();
+		ix->hk.K = h.K;
+		ix->hk.charBytes = h.hostKeyBytes;
+		if (h.hostKeyBytes) {
+			ix->hk.chars = static_cast<uint8_t*>(malloc(h.hostKeyBytes));
+			if (!ix->hk.chars) throw std::bad_alloc();
+			read_all(f.get(), ix->hk.chars, h.hostKeyBytes);
+		}
+		SSB_CUDA(cudaStreamSynchronize(ix->stream));
+		return ix.release();
+	}, nullptr);
+}
+
 SSB_API void ssb_index_destroy(ssb_index* ix)
 {
 	if (!ix) return;
 	guarded([&] {
 		cudaStream_t s = ix->stream;
 		delete ix;
-		if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+		if (s && !g_exiting.load()) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
 		return 0;
 	}, 0);
 }

@@ -24,6 +24,7 @@ namespace ssb {
 
 SearchWorkspace::~SearchWorkspace()
 {
+	if (g_exiting.load()) return;
 	if (ev0) cudaEventDestroy(ev0);
 	if (ev1) cudaEventDestroy(ev1);
 	if (ev2) cudaEventDestroy(ev2);

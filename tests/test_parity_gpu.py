@@ -485,3 +485,46 @@ def test_properties_full_size(ssb):
         exact = ix.search_batch(keys.slice(1000, 1064), 0.0, 5, strings=True)
         for i in range(64):
             assert exact.query(i)[3][0] == keys.get(1000 + i)
+
+
+def test_index_save_load_round_trip(ssb, oracle_built, tmp_path):
+    """a saved and re-loaded index has bit-identical tables and answers bit-identically (narrow with
+    descriptions + weights + short terms, and wide gSize=2)."""
+    from stringsearchlib_b200 import synth
+    words, w = synth.key_desc_rows(3000)
+    words = [words.get(i) for i in range(len(words))] + [b"LWMS", b"lw", b"LWM", b"x", None, b"  ", b"ab#c d", b"q"]
+    w = np.concatenate([w, np.linspace(0.5, 1.5, 8).astype(np.float32)])
+    S = oracle_built.SpecIndex(words, 2, w)
+    qs = [words[i] for i in range(0, 200, 2) if words[i]] + [b"LWMS", b"*", b"", b"l", b"lw", b"abc d"]
+    path = str(tmp_path / "narrow.ssbidx")
+    with ssb.Index(words, 2, w) as ix:
+        ix.set_valid_char(b".%$ @0123456789abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ#")
+        t0 = ix.tables()
+        r0 = ix.search_batch(qs, 0.0, 50, strings=True)
+        ix.save(path)
+    with ssb.Index.load(path) as ix2:
+        assert ix2.size() == S.size() and ix2.lib_size() == S.lib_size()
+        t1 = ix2.tables()
+        for k in t0:
+            if k == "info":
+                assert {a: b for a, b in t0[k].items() if a not in ("windows", "hashRetries")} == \
+                       {a: b for a, b in t1[k].items() if a not in ("windows", "hashRetries")}
+            else:
+                assert np.array_equal(t0[k], t1[k]), k
+        r1 = ix2.search_batch(qs, 0.0, 50, strings=True)
+        assert np.array_equal(r0.offsets, r1.offsets) and np.array_equal(r0.kids, r1.kids)
+        assert np.array_equal(r0.scores.view(np.uint32), r1.scores.view(np.uint32))
+        assert r0.strings == r1.strings
+    wk = synth.wide_keys(4000)
+    path2 = str(tmp_path / "wide.ssbidx")
+    with ssb.Index(wk, 1, None, 2) as ix:
+        q = synth.queries_from(wk, 64)
+        r0 = ix.search_batch(q, 0.0, 20, strings=True)
+        ix.save(path2)
+    with ssb.Index.load(path2) as ix2:
+        assert ix2.wide
+        r1 = ix2.search_batch(q, 0.0, 20, strings=True)
+        assert np.array_equal(r0.kids, r1.kids) and np.array_equal(r0.scores.view(np.uint32), r1.scores.view(np.uint32))
+        assert r0.strings == r1.strings
+    with pytest.raises(RuntimeError):
+        ssb.Index.load(str(tmp_path / "missing.ssbidx"))
