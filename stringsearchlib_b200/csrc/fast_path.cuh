@@ -190,16 +190,12 @@ __device__ void sort_buffer(SH& sh, uint32_t n)
 		}
 }
 
-// appends one key per calling lane; lanes that arrive together share one shared-memory atomic (opportunistic warp aggregation)
+// appends one key per calling lane. Appends are rare events by design (a handful of lanes at a time once tau is established),
+// so one shared-memory atomic per lane is cheaper than electing a leader and shuffling offsets around.
 template <class SH>
 __device__ __forceinline__ void append_key(SH& sh, unsigned long long key)
 {
-	const unsigned am = __activemask();
-	const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
-	uint32_t base = 0;
-	if (lane == leader) base = atomicAdd(&sh.bufCount, (uint32_t)__popc(am));
-	base = __shfl_sync(am, base, leader);
-	const uint32_t idx = base + __popc(am & ((1u << lane) - 1));
+	const uint32_t idx = atomicAdd(&sh.bufCount, 1u);
 	if (idx < sh.bufCap) sh.buf[idx] = key; else sh.overflow = 1;
 }
 
