@@ -16,8 +16,9 @@ const char* ssb_last_error(void);
 uint64_t ssb_kernel_launches(void);
 /* binds the engine to a CUDA device (default: current device). Call once per process, before any index. */
 int ssb_set_device(int device);
-/* which kernel answers the batched fast path first: 0 = k_fast_search (register K-way merge of the posting lists; default),
- * 1 = k_hash_search (duplicate detection by shared-memory hashing, falls back to 0 per query). Results are identical;
+/* which kernel answers the batched fast path first: 0 = k_fast_search (register K-way merge of the posting lists),
+ * 1 = k_hash_search (duplicate detection by shared-memory hashing, hands queries it cannot take to 0), -1 = the default
+ * (0, or 1 when the environment variable SSB_HASH is set). Results are identical;
  * the switch exists for measurements and for the parity tests that cover both. 0 on success. */
 int ssb_set_search_path(int path);
 

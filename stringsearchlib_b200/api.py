@@ -89,9 +89,9 @@ def kernel_launches():
 
 
 def set_search_path(path):
-    """0 = k_fast_search first (default), 1 = k_hash_search first; identical results (include/ssb_engine.h)."""
+    """0 = k_fast_search first, 1 = k_hash_search first, -1 = default (0 unless SSB_HASH is set); identical results (include/ssb_engine.h)."""
     if core_library().ssb_set_search_path(int(path)) != 0:
-        raise ValueError("search path must be 0 or 1")
+        raise ValueError("search path must be -1, 0 or 1")
 
 
 def set_device(device):

@@ -394,7 +394,7 @@ SSB_API const char* ssb_last_error(void) { return g_lastError.c_str(); }
 SSB_API uint64_t ssb_kernel_launches(void) { return g_kernel_launches.load(); }
 SSB_API int ssb_set_search_path(int path)
 {
-	if (path < 0 || path > 1) return -1;
+	if (path < -1 || path > 1) return -1;
 	g_search_path.store(path);
 	return 0;
 }

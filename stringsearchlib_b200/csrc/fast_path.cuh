@@ -22,6 +22,7 @@ constexpr uint32_t INF = 0xFFFFFFFFu;
 constexpr int FS_THREADS = 128;
 constexpr int FS_WIN = 6144;                            // posting slots per staged pass
 constexpr int FS_DEF_CAP = 128;                         // deferred (term, count) pairs per pass: candidates whose evaluation needs edges / string compares
+constexpr int FS_DEF_EXT = 1024;                        // ... on indexes with descriptions / weights, where every survivor is deferred (own array)
 constexpr int FS_REGION_PAD = 12;                        // per-list slack: 16-byte alignment shift (<=3) + bound slot + rounding
 constexpr int FS_WIN_ALLOC = FS_WIN + MAX_QGRAMS * FS_REGION_PAD + 16;
 constexpr int FS_BUF_MAX = 2 * FAST_KLIM;                // candidate buffer entries: 2 * limit rounded up to a power of two, chosen at launch
@@ -38,7 +39,8 @@ struct FastShared {
 	alignas(16) uint32_t win[FS_WIN_ALLOC];
 	unsigned long long* buf;                            // candidate buffer: bufCap entries behind this struct in dynamic smem
 	uint32_t bufCap;
-	uint32_t defCount;
+	uint32_t defCount, defCap;
+	unsigned long long* defList;                        // = deferred (aliases hist) or FS_DEF_EXT entries behind the candidate buffer
 	alignas(8) unsigned long long bar;                  // mbarrier of the stage buffer (TMA completion)
 	union {
 		unsigned long long deferred[FS_DEF_CAP];        // (count << 32 | term) pairs: live from the merge loop of a pass to the evaluation right after it
@@ -388,7 +390,7 @@ __device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__
 				if (key < tauNow) append_key(sh, key);
 			} else {
 				const uint32_t di = atomicAdd(&sh.defCount, 1u);
-				if (di < FS_DEF_CAP) sh.deferred[di] = (((unsigned long long)c) << 32) | m; else sh.overflow = 1;
+				if (di < sh.defCap) sh.defList[di] = (((unsigned long long)c) << 32) | m; else sh.overflow = 1;
 			}
 		}
 	}
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
                                                             uint32_t* __restrict__ denseList, uint32_t limit, uint32_t outStride,
                                                             uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
                                                             float* __restrict__ outScore, unsigned long long* __restrict__ statCounters,
-                                                            uint32_t bufCap, float threshold, uint32_t nIdx, uint32_t curIdx)
+                                                            uint32_t bufCap, float threshold, uint32_t nIdx, uint32_t curIdx, uint32_t defExt)
 {
 	// nIdx / curIdx: which counters hold this launch's list length and work cursor (the list is either every fast query or
 	// the ones k_hash_search handed over)
@@ -480,6 +482,8 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 		sh.ix = ix;
 		sh.buf = reinterpret_cast<unsigned long long*>(fs_smem + ((sizeof(FastShared) + 15) & ~size_t(15)));
 		sh.bufCap = bufCap;
+		sh.defList = defExt ? sh.buf + bufCap : sh.deferred;
+		sh.defCap = defExt ? defExt : (uint32_t)FS_DEF_CAP;
 		mbar_init(&sh.bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -543,8 +547,8 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 		bool tauReal = false;          // tau comes from a select over real candidates (not merely from the seed below)
 		uint32_t level = 0;
 		// small first pass when tau cannot be seeded: it only has to establish tau, and every survivor of it is a candidate
-		// (identity mode: at most bufCap appends; otherwise at most FS_DEF_CAP deferred evaluations)
-		const uint32_t firstCap = (ix.identity && ix.uniformW) ? min((uint32_t)FS_FIRST_PASS, bufCap) : (uint32_t)FS_DEF_CAP;
+		// (identity mode: at most bufCap appends; otherwise at most defCap deferred evaluations)
+		const uint32_t firstCap = (ix.identity && ix.uniformW) ? min((uint32_t)FS_FIRST_PASS, bufCap) : sh.defCap;
 		uint32_t cap = d.total > firstCap ? firstCap : FS_WIN;
 		if (ix.identity && ix.uniformW && d.cmin <= 1 && k <= FAST_KLIM && more) {
 			// Seed tau without a pass: the first k postings of any one list are k distinct keys (kid == term id) with at least
@@ -622,9 +626,9 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			else merge_dispatch<U, false, SHORT>(sh, qn, nLists);
 			__syncthreads();
 			{
-				const uint32_t nd = min(sh.defCount, (uint32_t)FS_DEF_CAP);
+				const uint32_t nd = min(sh.defCount, sh.defCap);
 				for (uint32_t i = tid; i < nd; i += FS_THREADS) {
-					const unsigned long long e = sh.deferred[i];
+					const unsigned long long e = sh.defList[i];
 					emit_candidate<U, SHORT>(sh, qn, (uint32_t)e, (uint32_t)(e >> 32));
 				}
 				if (nd) __syncthreads();
@@ -640,11 +644,14 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 				safeMode = true;
 				// (uniform weights + kid == term id: survivors are appended directly, only exact-match suspects are deferred)
 				cap = min((uint32_t)FS_WIN, bufCap - level);
-				if (!(ix.identity && ix.uniformW)) cap = min(cap, (uint32_t)FS_DEF_CAP);
+				if (!(ix.identity && ix.uniformW)) cap = min(cap, sh.defCap);
 				continue;
 			}
 			safeMode = false;
 			cap = FS_WIN;
+			// descriptions / weights: while single-gram matches cannot be rejected yet, (nearly) every posting of the pass is
+			// deferred -> keep the pass within the deferred list instead of overflowing it and redoing the pass
+			if (!(ix.identity && ix.uniformW) && sh.cmin <= 1 && (((unsigned long long)sh.hiKey[1]) << 32) < sh.tau) cap = min(cap, sh.defCap);
 			more = sh.lastPass == 0;
 			if (tid < MAX_QGRAMS && (uint32_t)tid < nLists) { sh.cur[tid] += sh.nTake[tid]; sh.rem[tid] -= sh.nTake[tid]; }
 			level = sh.bufCount;

@@ -515,16 +515,19 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	// footprint and with it the number of resident CTAs per SM (6 x 128 threads at limit <= 512)
 	uint32_t bufCap = 1024;
 	while (bufCap < 2 * std::min<uint32_t>(limit, FAST_KLIM)) bufCap <<= 1;
-	const size_t smemBytes = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)bufCap * 8;
+	// indexes with descriptions / weights defer every survivor of the merge (edge and weight look-ups): they get a deferred
+	// list of their own behind the candidate buffer instead of the small one that aliases the select histogram
+	const uint32_t defExt = (ix.identity && ix.uniformW) ? 0u : (uint32_t)FS_DEF_EXT;
+	const size_t smemBytes = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)bufCap * 8 + (size_t)defExt * 8;
 	static int numSMs = 0;
-	static int ctasFor[6] = {0, 0, 0, 0, 0, 0};
+	static int ctasFor[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 	const bool withShort = ix.nShort > 0;
-	const int cfg = (bufCap == 1024 ? 0 : (bufCap == 2048 ? 1 : 2)) + (withShort ? 3 : 0);
+	const int cfg = (bufCap == 1024 ? 0 : (bufCap == 2048 ? 1 : 2)) + (withShort ? 3 : 0) + (defExt ? 6 : 0);
 	if (!numSMs) {
 		int dev = 0;
 		SSB_CUDA(cudaGetDevice(&dev));
 		SSB_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
-		const int maxSmem = (int)(((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)FS_BUF_MAX * 8);
+		const int maxSmem = (int)(((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)FS_BUF_MAX * 8 + (size_t)FS_DEF_EXT * 8);
 		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
 		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
 		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
@@ -556,9 +559,13 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	SSB_CUDA(cudaEventRecord(ws.ev1, s));
 	// persistent grids: one wave of resident CTAs, queries handed out by an atomic cursor. k_hash_search takes the fast queries
 	// first (limit <= 512) and hands the ones it cannot answer to k_fast_search through fastList2.
-	static const bool envHash = getenv("SSB_HASH") != nullptr;
-	const int pathOpt = g_search_path.load(std::memory_order_relaxed);
-	const bool useHash = (pathOpt < 0 ? envHash : pathOpt == 1) && limit <= (uint32_t)HS_KLIM;
+	// Which kernel first? Measured (scripts/probe_configs.py, 4096 queries, ms per batch, merge vs hash): C4 headline 1.09 vs
+	// 1.88; C4 with threshold 0.3: 0.88 vs 1.10; C2 (descriptions + weights, threshold 0.3): 0.67 vs 0.97; C3 (wide): 0.03 vs
+	// 0.08. The register merge wins everywhere, so k_hash_search runs only on request (ssb_set_search_path / SSB_HASH).
+	static const int envPath = getenv("SSB_HASH") ? 1 : 0;
+	int pathOpt = g_search_path.load(std::memory_order_relaxed);
+	if (pathOpt < 0) pathOpt = envPath;
+	const bool useHash = pathOpt == 1 && limit <= (uint32_t)HS_KLIM;
 	if (useHash) {
 		static int hashCtas = 0;
 		const size_t hsBytes = ((sizeof(HashShared) + 15) & ~size_t(15)) + (size_t)1024 * 8;
@@ -583,11 +590,11 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	if (withShort)
 		k_fast_search<U, true><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, fl, ws.counters.get(),
 		                                                           ws.denseList.get(), limit, stride, ws.outCount.get(), ws.outKid.get(),
-		                                                           ws.outScore.get(), statCounters, bufCap, threshold, nIdx, curIdx);
+		                                                           ws.outScore.get(), statCounters, bufCap, threshold, nIdx, curIdx, defExt);
 	else
 		k_fast_search<U, false><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, fl, ws.counters.get(),
 		                                                            ws.denseList.get(), limit, stride, ws.outCount.get(), ws.outKid.get(),
-		                                                            ws.outScore.get(), statCounters, bufCap, threshold, nIdx, curIdx);
+		                                                            ws.outScore.get(), statCounters, bufCap, threshold, nIdx, curIdx, defExt);
 	SSB_LAUNCH_CHECK();
 	SSB_CUDA(cudaEventRecord(ws.ev2, s));
 

@@ -76,7 +76,7 @@ def check_search(ix, S, queries, threshold, limit, o=None):
                 assert np.array_equal(scores.view(np.uint32), sc[q, :n].view(np.uint32)), (path, q, scores[:8], sc[q, :8])
                 assert np.array_equal(kids, kid_of_ext[ext[q, :n]]), (path, q, kids[:8], kid_of_ext[ext[q, :8]])
     finally:
-        m.set_search_path(0)
+        m.set_search_path(-1)
     return r
 
 
@@ -478,7 +478,7 @@ def test_properties_full_size(ssb):
             r3 = ix.search_batch(q, 0.0, 100)
             _, _, st3 = ix.search_resident(nq, 0.0, 100)
         finally:
-            ssb.set_search_path(0)
+            ssb.set_search_path(-1)
         assert np.array_equal(r1.offsets, r3.offsets) and np.array_equal(r1.kids, r3.kids)
         assert np.array_equal(r1.scores.view(np.uint32), r3.scores.view(np.uint32))
         assert st3["nHash"] + st3["nHashHandover"] == nq and st3["nHash"] > nq // 2 and st3["nDense"] == 0, st3
