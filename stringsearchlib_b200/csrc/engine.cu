@@ -17,7 +17,15 @@ using namespace ssb;
 
 namespace {
 
-thread_local std::string g_lastError;
+// trivially destructible on purpose: thread-local destructors run at the very start of exit(), BEFORE the static registries of
+// the shim libraries destroy their remaining indexes through guarded() — a std::string here would be written to after its
+// buffer was freed (glibc: "corrupted double-linked list" at interpreter exit)
+thread_local char g_lastError[512] = {0};
+inline void set_last_error(const char* msg)
+{
+	strncpy(g_lastError, msg ? msg : "", sizeof(g_lastError) - 1);
+	g_lastError[sizeof(g_lastError) - 1] = 0;
+}
 
 struct EngineGlobals {
 	std::once_flag once;
@@ -312,13 +320,13 @@ ssb_batch* run_batch(ssb_index* ix, const void* units, const uint32_t* offsets, 
 template <class F> auto guarded(F f, decltype(f()) fail) -> decltype(f())
 {
 	try {
-		g_lastError.clear();
+		g_lastError[0] = 0;
 		return f();
 	} catch (const std::exception& e) {
-		g_lastError = e.what();
+		set_last_error(e.what());
 		fprintf(stderr, "[ssb] %s\n", e.what());
 	} catch (...) {
-		g_lastError = "unknown error";
+		set_last_error("unknown error");
 	}
 	return fail;
 }
@@ -390,7 +398,7 @@ extern "C" {
 
 #define SSB_API __attribute__((visibility("default")))
 
-SSB_API const char* ssb_last_error(void) { return g_lastError.c_str(); }
+SSB_API const char* ssb_last_error(void) { return g_lastError; }
 SSB_API uint64_t ssb_kernel_launches(void) { return g_kernel_launches.load(); }
 SSB_API int ssb_set_search_path(int path)
 {
