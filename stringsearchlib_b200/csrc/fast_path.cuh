@@ -545,6 +545,9 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 		// |q| <= gSize: the term scan below covers every long term and folds the gram path in, so no posting passes run
 		bool failed = false, safeMode = false, more = nLists != 0 && !scanLong;
 		bool tauReal = false;          // tau comes from a select over real candidates (not merely from the seed below)
+		// select again as soon as the buffer holds ~2k more candidates than needed: the sooner tau reaches the score class the
+		// k-th best lives in, the sooner the integer pre-filter stops whole classes (fewer appends, same number of selects)
+		const uint32_t selectAt = min(bufCap / 2, 2 * k + 64);
 		uint32_t level = 0;
 		// small first pass when tau cannot be seeded: it only has to establish tau, and every survivor of it is a candidate
 		// (identity mode: at most bufCap appends; otherwise at most defCap deferred evaluations)
@@ -621,12 +624,14 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			}
 			__syncthreads();
 			if (sh.overflow == 2) { failed = true; break; }
+			if (tid == 0) atomicAdd(&counters[16], 1u);
 			// ---- merge
 			if (sh.allOnes) merge_dispatch<U, true, SHORT>(sh, qn, nLists);
 			else merge_dispatch<U, false, SHORT>(sh, qn, nLists);
 			__syncthreads();
 			{
 				const uint32_t nd = min(sh.defCount, sh.defCap);
+				if (tid == 0 && nd) atomicAdd(&counters[19], nd);
 				for (uint32_t i = tid; i < nd; i += FS_THREADS) {
 					const unsigned long long e = sh.defList[i];
 					emit_candidate<U, SHORT>(sh, qn, (uint32_t)e, (uint32_t)(e >> 32));
@@ -637,6 +642,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 				// the optimistic pass overflowed the candidate buffer: roll it back, make room and redo it with a window small
 				// enough to be safe for single-edge terms; if that overflows too -> dense path
 				if (safeMode && level <= k) { failed = true; break; }
+				if (tid == 0) atomicAdd(&counters[17], 1u);
 				__syncthreads();
 				if (tid == 0) { sh.bufCount = level; sh.overflow = 0; }
 				__syncthreads();
@@ -660,7 +666,10 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			if (tid == 0) sh.passLo = nextLo;
 			// establish tau as soon as k candidates exist; afterwards the exact integer pre-filter keeps appends rare, so the
 			// (barrier-heavy) select only runs again when the buffer is half full
-			if (level > k && (!tauReal || level > bufCap / 2)) { select_smallest<FS_THREADS>(sh, level, k); level = k; tauReal = true; }
+			if (level > k && (!tauReal || level > selectAt)) {
+				select_smallest<FS_THREADS>(sh, level, k); level = k; tauReal = true;
+				if (tid == 0) atomicAdd(&counters[18], 1u);
+			}
 		}
 		// ---- edit-distance path: brute-force scan of the short terms (and of all terms for |q| <= gSize), hpp:232-254
 		if (SHORT && !failed && shortActive) {
@@ -672,7 +681,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 				if (sh.overflow) { failed = true; break; }
 				level = sh.bufCount;
 				__syncthreads();
-				if (level > k && (!tauReal || level > bufCap / 2)) { select_smallest<FS_THREADS>(sh, level, k); level = k; tauReal = true; }
+				if (level > k && (!tauReal || level > selectAt)) { select_smallest<FS_THREADS>(sh, level, k); level = k; tauReal = true; }
 			}
 			if (!failed) level = sh.bufCount;
 		}

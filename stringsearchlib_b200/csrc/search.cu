@@ -489,8 +489,8 @@ void ensure_workspace(SearchWorkspace& ws, uint32_t nq, size_t charBytes, uint32
 	if (!ws.ev0) {
 		SSB_CUDA(cudaEventCreate(&ws.ev0)); SSB_CUDA(cudaEventCreate(&ws.ev1));
 		SSB_CUDA(cudaEventCreate(&ws.ev2)); SSB_CUDA(cudaEventCreate(&ws.ev3));
-		ws.counters.alloc(16, s);
-		ws.hostCounters.reserve(16);
+		ws.counters.alloc(32, s);
+		ws.hostCounters.reserve(32);
 	}
 	if (nq > ws.capQ || stride > ws.stride) {
 		uint32_t cq = std::max(nq, ws.capQ), st = std::max(stride, ws.stride);
@@ -622,7 +622,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	};
 	if (csr) enqueue_finalize();
 	uint32_t* hc = ws.hostCounters.get();
-	SSB_CUDA(cudaMemcpyAsync(hc, ws.counters.get(), 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+	SSB_CUDA(cudaMemcpyAsync(hc, ws.counters.get(), 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 	SSB_CUDA(cudaEventRecord(ws.ev3, s));
 	SSB_CUDA(cudaEventSynchronize(ws.ev3));
 	const uint32_t nFast = hc[0], nDense = hc[1], nOverflow = hc[3];
@@ -654,6 +654,9 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	if (st) {
 		st->nFast = nFast; st->nDense = nDense; st->nOverflow = nOverflow;
 		st->nHash = hc[6]; st->nHashHandover = hc[5]; st->nHashGiveUp = hc[7];
+		if (getenv("SSB_DEBUG") && nFast)
+			fprintf(stderr, "[ssb] k_fast_search per query: %.1f passes, %.2f redone, %.1f selects, %.1f deferred evaluations\n", hc[16] / (double)nFast,
+			        hc[17] / (double)nFast, hc[18] / (double)nFast, hc[19] / (double)nFast);
 		if (hc[7] && getenv("SSB_DEBUG")) fprintf(stderr, "[ssb] k_hash_search gave up on %u queries: buffer %u, queue %u, other %u\n", hc[7], hc[13], hc[14], hc[15]);
 		st->postingsTouched = postings;
 		SSB_CUDA(cudaEventElapsedTime(&st->msDevice, ws.ev0, ws.ev3));
