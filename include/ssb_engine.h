@@ -69,6 +69,12 @@ ssb_batch* ssb_search_batch_packed(ssb_index* ix, const void* units, const uint3
                                    uint32_t limit);
 void ssb_batch_free(ssb_batch* b);
 
+/* One query, coalesced: concurrent callers on one index are answered together — whoever finds the index
+ * idle runs a batch, callers arriving meanwhile are collected into the next batch (per threshold / limit). Same result as
+ * ssb_search_batch with nq = 1; free with ssb_batch_free. The handle / guid shims route search() / score() through it. */
+ssb_batch* ssb_search_one(ssb_index* ix, const void* query, float threshold, uint32_t limit);
+void ssb_search_one_stats(const ssb_index* ix, uint64_t out[2]);   /* [0] calls, [1] batches run for them */
+
 /* uploads and answers a batch but leaves the per-shard results in HBM (multi-GPU: they go through ssb_export_records*
  * and the cross-shard merge instead of back to this host). 0 on success. */
 int ssb_search_batch_device(ssb_index* ix, const void* const* queries, uint32_t nq, float threshold, uint32_t limit);

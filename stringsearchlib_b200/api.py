@@ -77,6 +77,9 @@ def core_library():
     lib.ssb_merge_records_p2p_wait.argtypes = [c_void_p, c_uint32, c_uint32, c_uint32, POINTER(c_void_p), POINTER(c_void_p), c_uint32, c_uint32,
                                                c_void_p, c_uint32]
     lib.ssb_device_memset.argtypes = [c_void_p, c_int, c_uint64]
+    lib.ssb_search_one.argtypes = [c_void_p, c_void_p, c_float, c_uint32]
+    lib.ssb_search_one.restype = POINTER(_Batch)
+    lib.ssb_search_one_stats.argtypes = [c_void_p, POINTER(c_uint64)]
     lib.ssb_index_save.argtypes = [c_void_p, c_char_p]
     lib.ssb_index_load.argtypes = [c_char_p]
     lib.ssb_index_load.restype = c_void_p
@@ -318,6 +321,25 @@ class Index:
         """single query: [(key string, score)], like score() of the reference (dllmain.cpp:82)."""
         r = self.search_batch([query], threshold, limit, strings=True)
         return list(zip(r.strings, r.scores.tolist()))
+
+    def search_one(self, query, threshold=0.0, limit=100):
+        """ssb_search_one: one query through the coalescing front end (what the shims' search()/score() use);
+        returns (kids, scores) as numpy arrays."""
+        arr, keep = _as_pointer_array([query], self.wide)
+        bp = self._lib.ssb_search_one(self._h, arr[0], threshold, limit)
+        if not bp:
+            raise RuntimeError("ssb_search_one failed: " + self._lib.ssb_last_error().decode())
+        b = bp.contents
+        n = int(b.offsets[1])
+        kids = np.ctypeslib.as_array(b.kids, (max(n, 1),))[:n].copy()
+        scores = np.ctypeslib.as_array(b.scores, (max(n, 1),))[:n].copy()
+        self._lib.ssb_batch_free(bp)
+        return kids, scores
+
+    def search_one_stats(self):
+        a = (c_uint64 * 2)()
+        self._lib.ssb_search_one_stats(self._h, a)
+        return dict(calls=int(a[0]), batches=int(a[1]))
 
     def search_resident(self, nq, threshold=0.0, limit=100):
         """re-runs the device part of the last uploaded batch; returns (ms_device, ms_fast_kernel, stats dict)."""

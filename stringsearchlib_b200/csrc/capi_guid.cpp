@@ -74,7 +74,7 @@ void do_search(const char* guid, const C* query, C*** results, uint32_t* size, f
 		ssb_index_info(ix.get(), info);
 		if (!info[12] || info[11] != sizeof(C)) return;
 		const void* q = query;
-		ssb_batch* b = ssb_search_batch(ix.get(), &q, 1, threshold, limit);
+		ssb_batch* b = ssb_search_one(ix.get(), q, threshold, limit);      // concurrent callers coalesce into one GPU batch
 		if (!b) return;
 		const uint32_t n = b->offsets[1];
 		C** out = new C*[n];

@@ -31,7 +31,7 @@ uint32_t run(uint32_t handle, const char* query, char*** results, float** scores
 	ssb_index_info(ix.get(), info);
 	if (!info[12]) return 0;                                              // not indexed (nGramSearch.hpp:417,451)
 	const void* q = query;
-	ssb_batch* b = ssb_search_batch(ix.get(), &q, 1, threshold, limit);
+	ssb_batch* b = ssb_search_one(ix.get(), q, threshold, limit);      // concurrent callers coalesce into one GPU batch
 	if (!b) return 0;
 	const uint32_t n = b->offsets[1];
 	// nGramSearch.hpp:428-436 / 462-468: arrays from new[], strings alias index storage

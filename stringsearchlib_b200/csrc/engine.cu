@@ -5,7 +5,9 @@
 #include "index.h"
 #include "search.h"
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
 #include <cwchar>
 #include <memory>
@@ -148,6 +150,13 @@ struct ssb_index {
 	PinBuf<uint8_t> pinQ;     // pinned staging of packed queries
 	PinBuf<uint32_t> pinQOff;
 	SearchStats lastStats;
+	// coalescing front end of ssb_search_one: callers that arrive while a batch is running are answered together by the next one
+	struct OneReq { const void* q; float th; uint32_t limit; ssb_batch* out = nullptr; bool done = false; };
+	std::mutex oneMu;
+	std::condition_variable oneCv;
+	std::vector<OneReq*> onePending;
+	bool oneBusy = false;
+	std::atomic<uint64_t> oneCalls{0}, oneBatches{0};
 	~ssb_index()
 	{
 		if (stream && !g_exiting.load()) { cudaStreamSynchronize(stream); }
@@ -630,6 +639,58 @@ SSB_API ssb_batch* ssb_search_batch(ssb_index* ix, const void* const* queries, u
 			if (queries[q]) memcpy(ix->pinQ.get() + (size_t)off[q] * unit, queries[q], (size_t)(off[q + 1] - off[q]) * unit);
 		return run_batch(ix, ix->pinQ.get(), off, nq, threshold, limit);
 	}, nullptr);
+}
+// Single query with coalescing (the reference's intended usage is many threads calling search() under a
+// shared lock, dllmain.cpp:63). The first caller becomes the leader and runs a batch; callers that arrive meanwhile queue
+// up and are answered together by the next leader in ONE batch (same threshold / limit), so concurrent single calls get
+// batch throughput without any added latency when the index is idle.
+SSB_API ssb_batch* ssb_search_one(ssb_index* ix, const void* query, float threshold, uint32_t limit)
+{
+	if (!ix) return nullptr;
+	ssb_index::OneReq me{query, threshold, limit};
+	ix->oneCalls.fetch_add(1, std::memory_order_relaxed);
+	std::unique_lock<std::mutex> lk(ix->oneMu);
+	ix->onePending.push_back(&me);
+	while (!me.done) {
+		if (ix->oneBusy) { ix->oneCv.wait(lk); continue; }
+		// leader: everything pending with my parameters (my own request included) goes into one batch
+		ix->oneBusy = true;
+		std::vector<ssb_index::OneReq*> mine, rest;
+		for (auto* r : ix->onePending) ((r->th == me.th && r->limit == me.limit) ? mine : rest).push_back(r);
+		ix->onePending.swap(rest);
+		lk.unlock();
+		std::vector<const void*> qs(mine.size());
+		for (size_t i = 0; i < mine.size(); ++i) qs[i] = mine[i]->q;
+		ssb_batch* b = ssb_search_batch(ix, qs.data(), (uint32_t)qs.size(), threshold, limit);
+		ix->oneBatches.fetch_add(1, std::memory_order_relaxed);
+		if (b && mine.size() == 1) mine[0]->out = b;
+		else if (b) {
+			for (size_t i = 0; i < mine.size(); ++i) {             // hand every caller its own slice (heap arrays, like marshal())
+				const uint32_t o = b->offsets[i], n = b->offsets[i + 1] - o;
+				auto* impl = new BatchImpl();
+				ssb_batch* s = &impl->pub;
+				s->nq = 1;
+				s->offsets = new uint32_t[2]{0, n};
+				s->kids = new uint32_t[n ? n : 1]; s->scores = new float[n ? n : 1];
+				s->rows = new uint64_t[n ? n : 1]; s->strings = new const void*[n ? n : 1];
+				memcpy(s->kids, b->kids + o, (size_t)n * 4); memcpy(s->scores, b->scores + o, (size_t)n * 4);
+				memcpy(s->rows, b->rows + o, (size_t)n * 8); memcpy(s->strings, b->strings + o, (size_t)n * sizeof(void*));
+				mine[i]->out = s;
+			}
+			ssb_batch_free(b);
+		}
+		lk.lock();
+		for (auto* r : mine) r->done = true;
+		ix->oneBusy = false;
+		ix->oneCv.notify_all();
+	}
+	return me.out;
+}
+/* calls / batches of ssb_search_one since the index was created (how well concurrent callers coalesce) */
+SSB_API void ssb_search_one_stats(const ssb_index* ix, uint64_t out[2])
+{
+	out[0] = ix ? ix->oneCalls.load() : 0;
+	out[1] = ix ? ix->oneBatches.load() : 0;
 }
 SSB_API void ssb_batch_free(ssb_batch* b)
 {

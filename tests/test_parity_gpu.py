@@ -528,3 +528,65 @@ def test_index_save_load_round_trip(ssb, oracle_built, tmp_path):
         assert r0.strings == r1.strings
     with pytest.raises(RuntimeError):
         ssb.Index.load(str(tmp_path / "missing.ssbidx"))
+
+
+def test_concurrent_single_queries_coalesce(ssb, oracle_built):
+    """many threads calling the single-query entry point at once (the reference's intended usage,
+    dllmain.cpp:63) get exactly the single-threaded answers, and their calls are answered in shared batches — through
+    ssb_search_one directly and through score() of the as-shipped handle ABI."""
+    import threading
+    import time
+    from stringsearchlib_b200 import synth
+    n, nthreads, per = 20000, 16, 64
+    keys = synth.ascii_keys(n)
+    q = synth.queries_from(keys, nthreads * per)
+    queries = [q.get(i) for i in range(len(q))]
+    S = oracle_built.SpecIndex(keys, 1)
+    counts, ext, sc = S.search_batch(q, 0.0, 20)
+    kid_of_ext = S.tables()["kidOfExt"]
+    with ssb.Index(keys, 1) as ix:
+        got = [None] * len(queries)
+        errors = []
+
+        def work(t):
+            try:
+                for i in range(t * per, (t + 1) * per):
+                    got[i] = ix.search_one(queries[i], 0.0, 20)
+            except Exception as e:      # noqa: BLE001 - reported below
+                errors.append(e)
+
+        th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        dt = time.perf_counter() - t0
+        assert not errors, errors
+        for i in range(len(queries)):
+            c = int(counts[i])
+            kids, scores = got[i]
+            assert np.array_equal(kids, kid_of_ext[ext[i, :c]]), i
+            assert np.array_equal(scores.view(np.uint32), sc[i, :c].view(np.uint32)), i
+        st = ix.search_one_stats()
+        assert st["calls"] == len(queries) and st["batches"] <= st["calls"]
+        print(f"\n{len(queries)} concurrent single queries from {nthreads} threads: {len(queries) / dt:.0f} q/s, "
+              f"{st['calls'] / st['batches']:.1f} queries per GPU batch")
+    # the as-shipped ABI from several threads
+    words = [keys.get(i) for i in range(2000)]
+    H = ssb.HandleLibrary()
+    h = H.indexN(words, 1)
+    single = [H.score(h, queries[i], 0.0, 10) for i in range(64)]
+    out = [None] * 64
+
+    def work2(t):
+        for i in range(t * 8, (t + 1) * 8):
+            out[i] = H.score(h, queries[i], 0.0, 10)
+
+    th = [threading.Thread(target=work2, args=(t,)) for t in range(8)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert out == single
+    H.lib.dispose(h)
