@@ -402,6 +402,43 @@ __global__ void __launch_bounds__(256) k_finalize_csr(const uint32_t* __restrict
 	}
 }
 
+// tiny batches (<= 32 queries): clamp + scan + gather in ONE CTA that stores straight into the caller's pinned result arrays
+// and the pinned counters (zero-copy over PCIe) — a single search() call then costs two small uploads, a memset, three kernels
+// and one synchronisation instead of ~20 API calls
+__global__ void __launch_bounds__(256) k_finalize_tiny(const uint32_t* __restrict__ outCount, const uint32_t* __restrict__ outKid,
+                                                       const float* __restrict__ outScore, uint32_t nq, uint32_t stride,
+                                                       const uint32_t* __restrict__ keyOff, const uint64_t* __restrict__ keyRow,
+                                                       uint64_t strBase, uint32_t unit, uint32_t* __restrict__ counters,
+                                                       uint32_t* __restrict__ hOff, uint32_t* __restrict__ hKid, float* __restrict__ hScore,
+                                                       uint64_t* __restrict__ hRow, uint64_t* __restrict__ hStr, uint32_t* __restrict__ hCounters)
+{
+	__shared__ uint32_t off[33];
+	const uint32_t tid = threadIdx.x;
+	if (tid < 32) {
+		uint32_t c = tid < nq ? outCount[tid] : 0u;
+		const bool big = c > stride;                      // delivered out of band (dense path with limit > stride)
+		if (big) c = 0;
+		if (__any_sync(0xffffffffu, big) && tid == 0) counters[4] = 1;
+		uint32_t inc = c;
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= (uint32_t)o) inc += t; }
+		off[tid + 1] = inc;
+		if (tid == 0) off[0] = 0;
+	}
+	__syncthreads();
+	for (uint32_t q = 0; q < nq; ++q) {
+		const uint32_t o = off[q], n = off[q + 1] - o;
+		for (uint32_t i = tid; i < n; i += blockDim.x) {
+			const uint32_t kid = outKid[(size_t)q * stride + i];
+			hKid[o + i] = kid;
+			hScore[o + i] = outScore[(size_t)q * stride + i];
+			hRow[o + i] = keyRow[kid];
+			hStr[o + i] = strBase + (uint64_t)keyOff[kid] * unit;
+		}
+	}
+	if (tid <= nq) hOff[tid] = off[tid];
+	if (tid < 32) hCounters[tid] = counters[tid];
+}
+
 inline unsigned grid_for(size_t n, int tpb = 256) { return (unsigned)std::max<size_t>(1, (n + tpb - 1) / tpb); }
 
 template <class U>
@@ -544,7 +581,9 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	}
 	const int ctasPerSM = ctasFor[cfg];
 	unsigned long long* statCounters = reinterpret_cast<unsigned long long*>(ws.counters.get() + 8);
-	SSB_CUDA(cudaEventRecord(ws.ev0, s));
+	// tiny batch with pinned result arrays: see k_finalize_tiny (no events: nobody profiles a single query through them)
+	const bool tiny = hr && ix.K && nq <= 32 && hr->capQ >= nq && hr->capResults >= (size_t)nq * stride;
+	if (!tiny) SSB_CUDA(cudaEventRecord(ws.ev0, s));
 	ws.counters.zero(s);
 	const U* qc = reinterpret_cast<const U*>(ws.qchars.get());
 	U* qn = reinterpret_cast<U*>(ws.qnorm.get());
@@ -556,7 +595,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		k_order_fast<<<1, 1024, ORDER_MAX * 8, s>>>(ws.desc.get(), ws.fastList.get(), ws.counters.get());
 		SSB_LAUNCH_CHECK();
 	}
-	SSB_CUDA(cudaEventRecord(ws.ev1, s));
+	if (!tiny) SSB_CUDA(cudaEventRecord(ws.ev1, s));
 	// persistent grids: one wave of resident CTAs, queries handed out by an atomic cursor. k_hash_search takes the fast queries
 	// first (limit <= 512) and hands the ones it cannot answer to k_fast_search through fastList2.
 	// Which kernel first? Measured (scripts/probe_configs.py, 4096 queries, ms per batch, merge vs hash): C4 headline 1.09 vs
@@ -596,7 +635,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		                                                            ws.denseList.get(), limit, stride, ws.outCount.get(), ws.outKid.get(),
 		                                                            ws.outScore.get(), statCounters, bufCap, threshold, nIdx, curIdx, defExt);
 	SSB_LAUNCH_CHECK();
-	SSB_CUDA(cudaEventRecord(ws.ev2, s));
+	if (!tiny) SSB_CUDA(cudaEventRecord(ws.ev2, s));
 
 	// CSR finalisation (compaction + gather of row ids / string addresses) is enqueued speculatively, before the host
 	// knows whether any query needs the dense path: the common case costs ONE host synchronisation for small batches
@@ -620,11 +659,19 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		SSB_CUDA(cudaMemcpyAsync(hr->offsets, ws.csrOff.get(), (size_t)(nq + 1) * 4, cudaMemcpyDeviceToHost, s));
 		if (small) copy_arrays((size_t)nq * stride);
 	};
-	if (csr) enqueue_finalize();
 	uint32_t* hc = ws.hostCounters.get();
-	SSB_CUDA(cudaMemcpyAsync(hc, ws.counters.get(), 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-	SSB_CUDA(cudaEventRecord(ws.ev3, s));
-	SSB_CUDA(cudaEventSynchronize(ws.ev3));
+	if (tiny) {
+		k_finalize_tiny<<<1, 256, 0, s>>>(ws.outCount.get(), ws.outKid.get(), ws.outScore.get(), nq, stride, ix.keyOff.get(), ix.keyRow.get(),
+		                                  hr->strBase, (uint32_t)ix.unit, ws.counters.get(), hr->offsets, hr->kids, hr->scores, hr->rows,
+		                                  hr->strs, hc);
+		SSB_LAUNCH_CHECK();
+		SSB_CUDA(cudaStreamSynchronize(s));
+	} else {
+		if (csr) enqueue_finalize();
+		SSB_CUDA(cudaMemcpyAsync(hc, ws.counters.get(), 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		SSB_CUDA(cudaEventRecord(ws.ev3, s));
+		SSB_CUDA(cudaEventSynchronize(ws.ev3));
+	}
 	const uint32_t nFast = hc[0], nDense = hc[1], nOverflow = hc[3];
 	unsigned long long postings;
 	memcpy(&postings, hc + 8, 8);
@@ -654,13 +701,17 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	if (st) {
 		st->nFast = nFast; st->nDense = nDense; st->nOverflow = nOverflow;
 		st->nHash = hc[6]; st->nHashHandover = hc[5]; st->nHashGiveUp = hc[7];
-		if (getenv("SSB_DEBUG") && nFast)
+		static const bool dbg = getenv("SSB_DEBUG") != nullptr;
+		if (dbg && nFast)
 			fprintf(stderr, "[ssb] k_fast_search per query: %.1f passes, %.2f redone, %.1f selects, %.1f deferred evaluations\n", hc[16] / (double)nFast,
 			        hc[17] / (double)nFast, hc[18] / (double)nFast, hc[19] / (double)nFast);
-		if (hc[7] && getenv("SSB_DEBUG")) fprintf(stderr, "[ssb] k_hash_search gave up on %u queries: buffer %u, queue %u, other %u\n", hc[7], hc[13], hc[14], hc[15]);
+		if (hc[7] && dbg) fprintf(stderr, "[ssb] k_hash_search gave up on %u queries: buffer %u, queue %u, other %u\n", hc[7], hc[13], hc[14], hc[15]);
 		st->postingsTouched = postings;
-		SSB_CUDA(cudaEventElapsedTime(&st->msDevice, ws.ev0, ws.ev3));
-		SSB_CUDA(cudaEventElapsedTime(&st->msFastKernel, ws.ev1, ws.ev2));
+		st->msDevice = st->msFastKernel = 0;
+		if (!tiny) {
+			SSB_CUDA(cudaEventElapsedTime(&st->msDevice, ws.ev0, ws.ev3));
+			SSB_CUDA(cudaEventElapsedTime(&st->msFastKernel, ws.ev1, ws.ev2));
+		}
 	}
 }
 
