@@ -723,6 +723,8 @@ void search_batch(const DeviceIndex& ix, SearchWorkspace& ws, const void* qchars
 	out = BatchOutput();
 	out.nq = nq;
 	if (limit == 0) limit = 0x7FFFFFFFu;                                               // hpp:420-421,454-455
+	limit = std::min<uint32_t>(limit, std::max<uint32_t>(ix.K, 1u));                   // a result list never holds more than K keys: keeps
+	                                                                                   // "unlimited" queries on small indexes on the fast path
 	const uint32_t stride = std::min<uint32_t>(limit, FAST_KLIM);
 	out.stride = stride;
 	out.count.assign(nq, 0);
@@ -748,6 +750,7 @@ void search_batch_resident(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t 
                            SearchStats* stats)
 {
 	if (limit == 0) limit = 0x7FFFFFFFu;
+	limit = std::min<uint32_t>(limit, std::max<uint32_t>(ix.K, 1u));
 	if (!ix.indexed || nq == 0 || nq > ws.capQ) throw std::runtime_error("search_batch_resident: upload a batch with search_batch first");
 	const uint32_t stride = std::min<uint32_t>(limit, FAST_KLIM);
 	if (stride > ws.stride) throw std::runtime_error("search_batch_resident: limit larger than the uploaded batch's");
