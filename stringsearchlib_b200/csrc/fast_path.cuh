@@ -119,9 +119,11 @@ __device__ __forceinline__ void group_sync()
 	else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory");
 }
 
-// keeps the k smallest entries of buf[0..n) (all distinct), sets tau to the k-th smallest. CTA-wide.
-// MSD radix select over 8-bit digits; digits known to be zero in every entry are skipped: the high word is a score-class
-// rank < 256 in uniform-weight mode (topShift = 32), and kids have kidBits significant bits.
+// keeps the k smallest entries of buf[0..n) (all distinct), sets tau to (an upper bound without any entry in between of) the k-th
+// smallest. CTA-wide. MSD radix select over 8-bit digits; digits known to be zero in every entry are skipped: the high word
+// is a score-class rank < 256 in uniform-weight mode (topShift = 32), and kids have kidBits significant bits. Two barriers
+// per digit (warp 0 re-zeroes the bins it has just scanned); the select stops as soon as the bin that holds the k-th entry is
+// needed as a whole.
 template <int NT, int BAR = 0, class SH>
 __device__ void select_smallest(SH& sh, uint32_t n, uint32_t k)
 {
@@ -129,10 +131,11 @@ __device__ void select_smallest(SH& sh, uint32_t n, uint32_t k)
 	unsigned long long prefix = 0;
 	uint32_t kk = k;
 	const int topShift = sh.topShift, kidBits = sh.kidBits;
-	for (int shift = topShift; shift >= 0; shift -= 8) {
+	for (int i = tid; i < 256; i += NT) sh.hist[i] = 0;
+	group_sync<BAR, NT>();
+	int shift = topShift;
+	for (; shift >= 0; shift -= 8) {
 		if (shift < 32 && shift >= kidBits) { prefix <<= 8; continue; }      // this kid byte is zero everywhere
-		for (int i = tid; i < 256; i += NT) sh.hist[i] = 0;
-		group_sync<BAR, NT>();
 		for (uint32_t i = tid; i < n; i += NT) {
 			unsigned long long v = sh.buf[i];
 			if (shift == topShift || (v >> (shift + 8)) == prefix) atomicAdd(&sh.hist[(uint32_t)(v >> shift) & 255u], 1u);
@@ -141,7 +144,7 @@ __device__ void select_smallest(SH& sh, uint32_t n, uint32_t k)
 		if (tid < 32) {
 			uint32_t loc[8], sum = 0;
 #pragma unroll
-			for (int j = 0; j < 8; ++j) { loc[j] = sh.hist[tid * 8 + j]; sum += loc[j]; }
+			for (int j = 0; j < 8; ++j) { loc[j] = sh.hist[tid * 8 + j]; sh.hist[tid * 8 + j] = 0; sum += loc[j]; }
 			uint32_t inc = sum;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
@@ -150,7 +153,10 @@ __device__ void select_smallest(SH& sh, uint32_t n, uint32_t k)
 				uint32_t run = exc;
 #pragma unroll
 				for (int j = 0; j < 8; ++j) {
-					if (kk > run && kk <= run + loc[j]) { sh.selPrefixLo = tid * 8 + j; sh.selK = kk - run; }
+					if (kk > run && kk <= run + loc[j]) {
+						sh.selPrefixLo = tid * 8 + j;
+						sh.selK = (kk - run == loc[j]) ? 0u : kk - run;     // 0: every entry of this bin is among the k smallest
+					}
 					run += loc[j];
 				}
 			}
@@ -158,7 +164,10 @@ __device__ void select_smallest(SH& sh, uint32_t n, uint32_t k)
 		group_sync<BAR, NT>();
 		prefix = (prefix << 8) | sh.selPrefixLo;
 		kk = sh.selK;
+		if (kk == 0) break;
 	}
+	// stopped early: everything that starts with `prefix` is kept -> the bound is prefix followed by ones
+	if (shift > 0) prefix = (prefix << shift) | ((1ull << shift) - 1);
 	unsigned long long keep[FS_BUF_MAX / NT];
 	uint32_t nk = 0;
 	for (uint32_t i = tid; i < n; i += NT) {
