@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(1024) k_order_fast(const QDesc* __restrict__ d
 	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
 		const uint32_t q = fastList[i];
 		qs[i] = q;
-		bins[i] = desc[q].total;
+		// estimated work: the merge costs ~(4 + K) instructions per posting with K lists (min tree + one compare / advance per list)
+		bins[i] = (uint32_t)min((unsigned long long)desc[q].total * (4u + desc[q].nLists) >> 4, 0xFFFFFFFFull);
 		localMax = max(localMax, bins[i]);
 	}
 	for (int o = 16; o; o >>= 1) localMax = max(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
