@@ -554,9 +554,10 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 		// |q| <= gSize: the term scan below covers every long term and folds the gram path in, so no posting passes run
 		bool failed = false, safeMode = false, more = nLists != 0 && !scanLong;
 		bool tauReal = false;          // tau comes from a select over real candidates (not merely from the seed below)
-		// select again as soon as the buffer holds ~2k more candidates than needed: the sooner tau reaches the score class the
-		// k-th best lives in, the sooner the integer pre-filter stops whole classes (fewer appends, same number of selects)
-		const uint32_t selectAt = min(bufCap / 2, 2 * k + 64);
+		// the second select comes as soon as the buffer holds ~2k spare candidates: the sooner tau reaches the score class the
+		// k-th best lives in, the sooner the integer pre-filter stops whole classes. Later selects (long posting lists keep
+		// feeding better candidates) wait for a half-full buffer again, a select costs ~10 barriers.
+		uint32_t selectAt = min(bufCap / 2, 2 * k + 64);
 		uint32_t level = 0;
 		// small first pass when tau cannot be seeded: it only has to establish tau, and every survivor of it is a candidate
 		// (identity mode: at most bufCap appends; otherwise at most defCap deferred evaluations)
@@ -676,6 +677,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			// establish tau as soon as k candidates exist; afterwards the exact integer pre-filter keeps appends rare, so the
 			// (barrier-heavy) select only runs again when the buffer is half full
 			if (level > k && (!tauReal || level > selectAt)) {
+				if (tauReal) selectAt = bufCap / 2;
 				select_smallest<FS_THREADS>(sh, level, k); level = k; tauReal = true;
 				if (tid == 0) atomicAdd(&counters[18], 1u);
 			}
