@@ -101,6 +101,13 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 	return v;
 }
 
+// if (head == m) { pos += 4; head = *pos; } as two predicated instructions that update the cursor in place (the C++ form
+// made ptxas compute pos + 4 into a temporary and copy it back: one extra MOV per list and term)
+__device__ __forceinline__ void advance_if_head(uint32_t& pos, uint32_t& head, uint32_t m)
+{
+	asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 4;\n\t@p ld.shared.u32 %1, [%0];\n\t}" : "+r"(pos), "+r"(head) : "r"(m) : "memory");
+}
+
 __device__ __forceinline__ uint32_t lower_bound_smem(const uint32_t* a, uint32_t n, uint32_t x)
 {
 	uint32_t lo = 0, hi = n;
@@ -361,6 +368,9 @@ __device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__
 	const bool identMode = sh.ix.identity && sh.ix.uniformW;
 	const unsigned long long tauNow = sh.tau;
 	const uint32_t cpromNow = sh.cprom;
+	uint32_t posSumPrev = 0;
+#pragma unroll
+	for (int i = 0; i < KT; ++i) posSumPrev += pos[i];
 	while (true) {
 		uint32_t m = head[0];
 #pragma unroll
@@ -368,21 +378,17 @@ __device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__
 		if (m >= hi) break;
 		uint32_t c = 0;
 		if (ONES) {
-			// count = number of cursors that advance = (sum of cursor addresses after - before) / 4: the adds fold into
-			// 3-input IADD3s, cheaper than one predicated increment per list
-			uint32_t before = 0, after = 0;
+			// count = number of cursors that advance = (sum of the cursor addresses now - after the previous term) / 4: the
+			// adds fold into 3-input IADD3s (cheaper than one predicated increment per list), and carrying the sum from term
+			// to term means the cursors are updated in place (a before/after pair made the compiler keep two copies of
+			// every cursor: ~2 MOVs per list and term)
 #pragma unroll
-			for (int i = 0; i < KT; ++i) before += pos[i];
+			for (int i = 0; i < KT; ++i) advance_if_head(pos[i], head[i], m);
+			uint32_t posSum = 0;
 #pragma unroll
-			for (int i = 0; i < KT; ++i) {
-				if (head[i] == m) {
-					pos[i] += 4;
-					head[i] = lds_u32(pos[i]);
-				}
-			}
-#pragma unroll
-			for (int i = 0; i < KT; ++i) after += pos[i];
-			c = (after - before) >> 2;
+			for (int i = 0; i < KT; ++i) posSum += pos[i];
+			c = (posSum - posSumPrev) >> 2;
+			posSumPrev = posSum;
 		} else {
 #pragma unroll
 			for (int i = 0; i < KT; ++i) {
