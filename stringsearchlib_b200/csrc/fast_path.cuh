@@ -621,9 +621,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 				}
 				if (lane == 0) {
 					sh.passHi = bound == INF ? last + 1 : bound;
-					uint32_t top = 0;
-					if (best) { top = 1; while ((top << 1) <= best) top <<= 1; }
-					sh.searchTop = top;
+					sh.searchTop = best ? 1u << (31 - __clz(best)) : 0u;        // largest power of two <= the longest window
 					// integer pre-filter: a count c <= cRej can neither pass the threshold nor beat the running k-th best.
 					// In identity mode kid == term id >= passLo, which makes the bound exact for the tie class of tau.
 					uint32_t rej = sh.cmin ? sh.cmin - 1 : 0;
