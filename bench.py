@@ -439,7 +439,9 @@ def main():
             "ms_per_step": step_ms, "wall_ms_per_step": 1e3 * float(np.mean(step_s)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * float(np.mean(e2e_s))},
+                    "ms_per_step": 1e3 * float(np.mean(e2e_s)),
+                    "delivery": "N=1: k_fast_search stores each finished query straight into the pinned ssb_batch arrays (device-to-host "
+                                "over PCIe, overlapped with the kernel) when every query fills its limit; otherwise compaction + copies"},
             "gpu_launches": int(launches),   # kernels launched in the timed region (each step runs the path twice: e2e + resident)
             "queries_by_kernel": {"k_hash_search": last_st.get("nHash", 0), "k_fast_search": last_st.get("nHashHandover", 0),
                                   "dense": last_st.get("nDense", 0)},

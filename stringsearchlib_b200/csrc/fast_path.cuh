@@ -28,6 +28,17 @@ constexpr int FS_WIN_ALLOC = FS_WIN + MAX_QGRAMS * FS_REGION_PAD + 16;
 constexpr int FS_BUF_MAX = 2 * FAST_KLIM;                // candidate buffer entries: 2 * limit rounded up to a power of two, chosen at launch
 constexpr int FS_FIRST_PASS = 2048;                      // small first pass: establishes tau early
 
+// Pinned result arrays of the caller (device-accessible host memory): with a fixed number of results per query the CSR layout
+// of an ssb_batch is the fixed-stride layout, so every CTA can store a finished query straight to the host while the others
+// keep searching — the result copy overlaps the kernel instead of following it. kids == nullptr: off.
+struct HostOut {
+	uint32_t* kids;
+	float* scores;
+	uint64_t* rows;
+	uint64_t* strs;
+	uint64_t strBase;
+};
+
 struct PassPlan {
 	uint32_t wbase[MAX_QGRAMS];     // element offset of list i's window inside the stage buffer
 	uint32_t avail[MAX_QGRAMS];     // postings of list i that may be consumed in this pass: min(rem, wmax)
@@ -483,7 +494,8 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
                                                             uint32_t* __restrict__ denseList, uint32_t limit, uint32_t outStride,
                                                             uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
                                                             float* __restrict__ outScore, unsigned long long* __restrict__ statCounters,
-                                                            uint32_t bufCap, float threshold, uint32_t nIdx, uint32_t curIdx, uint32_t defExt)
+                                                            uint32_t bufCap, float threshold, uint32_t nIdx, uint32_t curIdx, uint32_t defExt,
+                                                            HostOut ho)
 {
 	// nIdx / curIdx: which counters hold this launch's list length and work cursor (the list is either every fast query or
 	// the ones k_hash_search handed over)
@@ -712,13 +724,23 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 		sort_buffer<FS_THREADS>(sh, level);
 		for (uint32_t i = tid; i < level; i += FS_THREADS) {
 			unsigned long long v = sh.buf[i];
-			outKid[(size_t)q * outStride + i] = (uint32_t)v;
+			const uint32_t kid = (uint32_t)v;
 			const uint32_t hi = (uint32_t)(v >> 32);
-			outScore[(size_t)q * outStride + i] = sh.classMode ? (hi == 0 ? 100.0f : edge_value(1.0f, sh.sOf[nGrams - hi + 1])) : rank_key_score(v);
+			const float score = sh.classMode ? (hi == 0 ? 100.0f : edge_value(1.0f, sh.sOf[nGrams - hi + 1])) : rank_key_score(v);
+			const size_t o = (size_t)q * outStride + i;
+			outKid[o] = kid;
+			outScore[o] = score;
+			if (ho.kids) {
+				ho.kids[o] = kid;
+				ho.scores[o] = score;
+				ho.rows[o] = ix.keyRow[kid];
+				ho.strs[o] = ho.strBase + (uint64_t)ix.keyOff[kid] * (uint32_t)ix.unit;
+			}
 		}
 		if (tid == 0) {
 			outCount[q] = level;
 			atomicAdd(&statCounters[0], (unsigned long long)d.total);
+			if (level != outStride) atomicAdd(&counters[22], 1u);      // a short result list: the host arrays need compaction
 		}
 	}
 }

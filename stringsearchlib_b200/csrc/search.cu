@@ -624,17 +624,23 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		                                                    statCounters, 1024u, threshold);
 		SSB_LAUNCH_CHECK();
 	}
+	// direct delivery (see HostOut): possible when the caller gave pinned CSR arrays, the stride is the limit itself and only
+	// k_fast_search writes results; it holds if every query turns out to fill its `limit` slots (checked after the kernel)
+	const bool direct = !tiny && !useHash && hr && ix.K && hr->capQ >= nq && hr->capResults >= (size_t)nq * stride && stride == limit &&
+	                    (size_t)nq * stride < (1ull << 32);
+	HostOut ho{};
+	if (direct) { ho.kids = hr->kids; ho.scores = hr->scores; ho.rows = hr->rows; ho.strs = reinterpret_cast<uint64_t*>(hr->strs); ho.strBase = hr->strBase; }
 	const uint32_t* fl = useHash ? ws.fastList2.get() : ws.fastList.get();
 	const uint32_t nIdx = useHash ? 5u : 0u, curIdx = useHash ? 12u : 2u;
 	const unsigned grid = (unsigned)std::min<size_t>((size_t)numSMs * ctasPerSM, std::max<uint32_t>(nq, 1));
 	if (withShort)
 		k_fast_search<U, true><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, fl, ws.counters.get(),
 		                                                           ws.denseList.get(), limit, stride, ws.outCount.get(), ws.outKid.get(),
-		                                                           ws.outScore.get(), statCounters, bufCap, threshold, nIdx, curIdx, defExt);
+		                                                           ws.outScore.get(), statCounters, bufCap, threshold, nIdx, curIdx, defExt, ho);
 	else
 		k_fast_search<U, false><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, fl, ws.counters.get(),
 		                                                            ws.denseList.get(), limit, stride, ws.outCount.get(), ws.outKid.get(),
-		                                                            ws.outScore.get(), statCounters, bufCap, threshold, nIdx, curIdx, defExt);
+		                                                            ws.outScore.get(), statCounters, bufCap, threshold, nIdx, curIdx, defExt, ho);
 	SSB_LAUNCH_CHECK();
 	if (!tiny) SSB_CUDA(cudaEventRecord(ws.ev2, s));
 
@@ -668,10 +674,21 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		SSB_LAUNCH_CHECK();
 		SSB_CUDA(cudaStreamSynchronize(s));
 	} else {
-		if (csr) enqueue_finalize();
+		if (csr && !direct) enqueue_finalize();
 		SSB_CUDA(cudaMemcpyAsync(hc, ws.counters.get(), 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 		SSB_CUDA(cudaEventRecord(ws.ev3, s));
 		SSB_CUDA(cudaEventSynchronize(ws.ev3));
+	}
+	bool delivered = false;
+	if (direct) {
+		if (hc[0] == nq && hc[1] == 0 && hc[22] == 0) {
+			// every query is a fast query with exactly `limit` results: the stores of the kernel ARE the CSR arrays
+			for (uint32_t q = 0; q <= nq; ++q) hr->offsets[q] = q * stride;
+			delivered = true;
+		} else if (hc[1] == 0) {
+			enqueue_finalize();                       // some list is short: compact on the device as usual
+			SSB_CUDA(cudaStreamSynchronize(s));
+		}
 	}
 	const uint32_t nFast = hc[0], nDense = hc[1], nOverflow = hc[3];
 	unsigned long long postings;
@@ -693,7 +710,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		}
 	}
 	if (csr && out && out->big.empty()) {
-		if (!small) {
+		if (!small && !delivered) {
 			const size_t total = hr->offsets[nq];
 			if (total) { copy_arrays(total); SSB_CUDA(cudaStreamSynchronize(s)); }
 		}
