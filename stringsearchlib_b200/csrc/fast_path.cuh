@@ -631,17 +631,21 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 					best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
 					last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
 				}
+				// integer pre-filter: a count c <= cRej can neither pass the threshold nor beat the running k-th best. In identity
+				// mode kid == term id >= passLo, which makes the bound exact for the tie class of tau. Lane j tests count
+				// rej0 + 1 + j (nGrams <= 32 = one warp); cRej = rej0 + the leading run of rejectable counts.
+				uint32_t rej = sh.cmin ? sh.cmin - 1 : 0;
+				{
+					const unsigned long long tau = sh.tau;
+					const unsigned long long lowKid = (sh.ix.identity && sh.ix.uniformW) ? sh.passLo : 0u;
+					const uint32_t c = rej + 1 + lane;
+					const bool out = c <= nGrams && ((((unsigned long long)sh.hiKey[min(c, (uint32_t)MAX_QGRAMS)]) << 32) | lowKid) >= tau;
+					const unsigned mOut = __ballot_sync(0xffffffffu, out);
+					rej += mOut == 0xffffffffu ? 32u : (uint32_t)__ffs(~mOut) - 1;
+				}
 				if (lane == 0) {
 					sh.passHi = bound == INF ? last + 1 : bound;
 					sh.searchTop = best ? 1u << (31 - __clz(best)) : 0u;        // largest power of two <= the longest window
-					// integer pre-filter: a count c <= cRej can neither pass the threshold nor beat the running k-th best.
-					// In identity mode kid == term id >= passLo, which makes the bound exact for the tie class of tau.
-					uint32_t rej = sh.cmin ? sh.cmin - 1 : 0;
-					const unsigned long long tau = sh.tau;
-					const unsigned long long lowKid = (sh.ix.identity && sh.ix.uniformW) ? sh.passLo : 0u;
-					for (uint32_t c = rej + 1; c <= nGrams; ++c) {
-						if (((((unsigned long long)sh.hiKey[c]) << 32) | lowKid) >= tau) rej = c; else break;
-					}
 					sh.cRej = rej;
 					sh.defCount = 0;
 					sh.lastPass = bound == INF;
