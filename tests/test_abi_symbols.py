@@ -74,3 +74,20 @@ def test_product_does_not_reference_the_oracle():
                     if re.search(r"(import|from)\s+oracle|oracle/_ref|libspec|libref|ngram_spec", t):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_host_only_entry_points_behave_without_gpu(tmp_path):
+    """entry points that need no device work validate their arguments and fail loudly (never silently) without a GPU"""
+    import sys
+    sys.path.insert(0, ROOT)
+    import stringsearchlib_b200 as ssb
+    for path in (-1, 0, 1, -1):
+        ssb.set_search_path(path)
+    with pytest.raises(ValueError):
+        ssb.set_search_path(2)
+    junk = tmp_path / "junk.ssbidx"
+    junk.write_bytes(b"not an index file" * 8)
+    with pytest.raises(RuntimeError):
+        ssb.Index.load(str(junk))                      # bad magic on a GPU box, CUDA initialisation error without one
+    with pytest.raises(RuntimeError):
+        ssb.Index.load(str(tmp_path / "missing.ssbidx"))
