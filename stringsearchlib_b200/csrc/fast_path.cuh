@@ -696,7 +696,16 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			if (tid == 0) sh.passLo = nextLo;
 			// establish tau as soon as k candidates exist; afterwards the exact integer pre-filter keeps appends rare, so the
 			// (barrier-heavy) select only runs again when the buffer is half full
-			if (level > k && (!tauReal || level > selectAt)) {
+			if (level > k && !tauReal && sh.classMode && (uint32_t)(sh.tau >> 32) == sh.exactKey[1] && level <= bufCap / 4) {
+				// first candidates after a seeded tau (the short first pass): all `level` >= k of them have a kid below this
+				// pass's end, so (count-1 class, end of the pass) bounds the k-th best — as good as a select for stopping the
+				// single-list terms of the passes to come, and free
+				if (tid == 0) {
+					const unsigned long long t2 = (((unsigned long long)sh.exactKey[1]) << 32) | nextLo;
+					if (t2 < sh.tau) sh.tau = t2;
+				}
+				tauReal = true;
+			} else if (level > k && (!tauReal || level > selectAt)) {
 				if (tauReal) selectAt = bufCap / 2;
 				select_smallest<FS_THREADS>(sh, level, k); level = k; tauReal = true;
 				if (tid == 0) atomicAdd(&counters[18], 1u);
