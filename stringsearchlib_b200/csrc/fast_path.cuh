@@ -67,6 +67,7 @@ struct FastShared {
 	unsigned long long tau;
 	uint32_t promotedKey;              // key high word of an exact match (score 100)
 	uint32_t bufCount, overflow, query, selPrefixLo, selK;
+	uint32_t nGe2;                     // candidates appended so far with a match count >= 2 (uniform-weight mode)
 	uint32_t passLo, passHi, searchTop, cRej, lastPass, prefetched;
 	uint32_t qlen, nGrams, cmin, cprom, allOnes, nLists, total;
 	uint32_t shortActive, scanLong;    // the edit-distance path runs for this query / it also covers every long term
@@ -413,7 +414,10 @@ __device__ __forceinline__ void merge_pass(FastShared& sh, const U* __restrict__
 		if (c > cRej) {
 			if (identMode && c < cpromNow) {
 				const unsigned long long key = (((unsigned long long)sh.exactKey[c]) << 32) | m;
-				if (key < tauNow) append_key(sh, key);
+				if (key < tauNow) {
+					append_key(sh, key);
+					if (c >= 2) atomicAdd(&sh.nGe2, 1u);
+				}
 			} else {
 				const uint32_t di = atomicAdd(&sh.defCount, 1u);
 				if (di < sh.defCap) sh.defList[di] = (((unsigned long long)c) << 32) | m; else sh.overflow = 1;
@@ -554,7 +558,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			}
 		}
 		if (tid == 0) {
-			sh.bufCount = 0; sh.overflow = 0; sh.tau = ~0ull; sh.passLo = 0; sh.prefetched = 0;
+			sh.bufCount = 0; sh.overflow = 0; sh.tau = ~0ull; sh.passLo = 0; sh.prefetched = 0; sh.nGe2 = 0;
 			sh.qlen = d.qlen; sh.nGrams = nGrams; sh.cmin = d.cmin; sh.cprom = d.cprom; sh.nLists = nLists; sh.total = d.total;
 			sh.classMode = classMode;
 			sh.shortActive = shortActive; sh.scanLong = scanLong; sh.scanLongOnly = 0; sh.threshold = threshold;
@@ -705,6 +709,14 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 					if (t2 < sh.tau) sh.tau = t2;
 				}
 				tauReal = true;
+			} else if (tauReal && sh.classMode && nGrams >= 2 && sh.nGe2 >= k && (uint32_t)(sh.tau >> 32) > sh.exactKey[2] &&
+			           level <= bufCap / 2) {
+				// k candidates with two or more matches are known, all below this pass's end: (count-2 class, end of the pass)
+				// bounds the k-th best — tau moves into the class it will end in without a select, and the passes to come
+				// stop their two-match terms in the integer pre-filter
+				__syncthreads();                    // every thread has read tau for the test above before it changes class
+				if (tid == 0) sh.tau = (((unsigned long long)sh.exactKey[2]) << 32) | nextLo;
+				selectAt = bufCap / 2;
 			} else if (level > k && (!tauReal || level > selectAt)) {
 				if (tauReal) selectAt = bufCap / 2;
 				select_smallest<FS_THREADS>(sh, level, k); level = k; tauReal = true;
