@@ -440,13 +440,14 @@ def main():
             "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(np.mean(e2e_s)),
-                    "delivery": "N=1: k_fast_search stores each finished query straight into the pinned ssb_batch arrays (device-to-host "
+                    "delivery": "N=1: the search kernel stores each finished query straight into the pinned ssb_batch arrays (device-to-host "
                                 "over PCIe, overlapped with the kernel) when every query fills its limit; otherwise compaction + copies"},
             "gpu_launches": int(launches),   # kernels launched in the timed region (each step runs the path twice: e2e + resident)
-            "queries_by_kernel": {"k_hash_search": last_st.get("nHash", 0), "k_fast_search": last_st.get("nHashHandover", 0),
+            "queries_by_kernel": {"k_sieve_search": last_st.get("nSieve", 0),
+                                  "k_fast_search": last_st.get("nFast", 0) - last_st.get("nSieve", 0),
                                   "dense": last_st.get("nDense", 0)},
-            "roofline": {"bound": "hbm", "kernel": "k_hash_search" if last_st.get("nHash", 0) * 2 > args.batch else "k_fast_search",
-                         "timed": "k_hash_search + k_fast_search launches of one batch (CUDA events on the engine's stream)",
+            "roofline": {"bound": "hbm", "kernel": "k_sieve_search" if last_st.get("nSieve", 0) * 2 > args.batch else "k_fast_search",
+                         "timed": "k_sieve_search + k_fast_search launches of one batch (CUDA events on the engine's stream)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms},

@@ -14,7 +14,7 @@ def run(name, ix, q, th, limit):
         for _ in range(5):
             ms, msk, st = ix.search_resident(len(q), th, limit)
             best = min(best, msk)
-        out.append((path, round(best, 4), st["nHash"], st["nHashHandover"], st["nDense"]))
+        out.append((path, round(best, 4), st["nSieve"], st["nSieveHandover"], st["nDense"]))
     ssb.set_search_path(-1)
     print(name, out, flush=True)
 

@@ -757,6 +757,11 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 	}
 	if (st) { SSB_CUDA(cudaStreamSynchronize(s)); st->msGrams = tPhase.lap(); }
 
+	// ---- sieve: block bitmaps over the posting lists (derived; sieve.cu)
+	ix.indexed = true;                                          // hpp:45
+	build_sieve(ix, s);
+	if (st) { SSB_CUDA(cudaStreamSynchronize(s)); st->msSieve = tPhase.lap(); }
+
 	// ---- properties + host key table
 	Props hp = d2h_scalar(props.get(), s);
 	ix.identity = !hp.notIdentity && T == K && E == T;
@@ -785,7 +790,6 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 		}
 		for (auto& t : th) t.join();
 	}
-	ix.indexed = true;                                          // hpp:45
 	if (st) { st->msD2H = tPhase.lap(); st->msTotal = tAll.lap(); }
 }
 

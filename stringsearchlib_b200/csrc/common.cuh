@@ -32,9 +32,10 @@ inline std::atomic<uint64_t> g_kernel_launches{0};
 // that are still alive then (cached staging buffers, indexes a host never disposed of) must not call into a CUDA runtime
 // that is tearing down — the process is about to return everything to the OS anyway
 inline std::atomic<bool> g_exiting{false};
-// which kernel answers the fast queries first: 0 = k_fast_search (register K-way merge), 1 = k_hash_search (duplicate detection
-// by hashing; hands what it cannot take to k_fast_search). Both are exact; DESIGN.md §4.2 has the measurements behind the default.
-inline std::atomic<int> g_search_path{-1};       // -1: default (0, or 1 when SSB_HASH is set in the environment)
+// which kernel answers the fast queries first: 1 = k_sieve_search (block bitmaps, reads only the postings of blocks that can
+// matter; hands what it does not take to k_fast_search), 0 = k_fast_search alone (register K-way merge of the posting lists).
+// Both are exact; DESIGN.md §4.2 has the measurements behind the default.
+inline std::atomic<int> g_search_path{-1};       // -1: default (1, or 0 when SSB_MERGE is set in the environment)
 #define SSB_LAUNCH_CHECK() (::ssb::g_kernel_launches.fetch_add(1, std::memory_order_relaxed), \
                             ::ssb::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__))
 

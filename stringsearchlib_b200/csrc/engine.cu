@@ -494,6 +494,7 @@ SSB_API ssb_index* ssb_index_load(const char* path)
 			if (!ix->hk.chars) throw std::bad_alloc();
 			read_all(f.get(), ix->hk.chars, h.hostKeyBytes);
 		}
+		build_sieve(d, ix->stream);                               // derived data: not in the file
 		SSB_CUDA(cudaStreamSynchronize(ix->stream));
 		return ix.release();
 	}, nullptr);
@@ -541,7 +542,7 @@ SSB_API void ssb_index_build_ms(const ssb_index* ix, double ms[8])
 	memset(ms, 0, 8 * sizeof(double));
 	if (!ix) return;
 	ms[0] = ix->bst.msTotal + ix->msPack; ms[1] = ix->msPack; ms[2] = ix->bst.msH2D; ms[3] = ix->bst.msIntern; ms[4] = ix->bst.msEdges;
-	ms[5] = ix->bst.msGrams; ms[6] = ix->bst.msD2H;
+	ms[5] = ix->bst.msGrams; ms[6] = ix->bst.msD2H; ms[7] = ix->bst.msSieve;
 }
 SSB_API int ssb_index_copy(const ssb_index* ix, int which, void* dst, uint64_t bytes)
 {
@@ -711,7 +712,7 @@ SSB_API int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uin
 		if (ms) { ms[0] = st.msDevice; ms[1] = st.msFastKernel; }
 		if (stats) {
 			stats[0] = st.nFast; stats[1] = st.nDense; stats[2] = st.nOverflow; stats[3] = st.postingsTouched;
-			stats[4] = st.nHash; stats[5] = st.nHashHandover; stats[6] = st.nHashGiveUp; stats[7] = 0;
+			stats[4] = st.nSieve; stats[5] = st.nSieveHandover; stats[6] = st.nSieveGiveUp; stats[7] = 0;
 		}
 		return 0;
 	}, -1);

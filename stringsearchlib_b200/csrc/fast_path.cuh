@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
                                                             HostOut ho)
 {
 	// nIdx / curIdx: which counters hold this launch's list length and work cursor (the list is either every fast query or
-	// the ones k_hash_search handed over)
+	// the ones k_sieve_search handed over)
 	extern __shared__ __align__(16) unsigned char fs_smem[];
 	FastShared& sh = *reinterpret_cast<FastShared*>(fs_smem);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -581,6 +581,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 		// feeding better candidates) wait for a half-full buffer again, a select costs ~10 barriers.
 		uint32_t selectAt = min(bufCap / 2, 2 * k + 64);
 		uint32_t level = 0;
+		uint32_t levelGe2 = 0;         // sh.nGe2 at the start of the pass in flight (restored together with bufCount when a pass is redone)
 		// small first pass when tau cannot be seeded: it only has to establish tau, and every survivor of it is a candidate
 		// (identity mode: at most bufCap appends; otherwise at most defCap deferred evaluations)
 		const uint32_t firstCap = (ix.identity && ix.uniformW) ? min((uint32_t)FS_FIRST_PASS, bufCap) : sh.defCap;
@@ -678,7 +679,8 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 				if (safeMode && level <= k) { failed = true; break; }
 				if (tid == 0) atomicAdd(&counters[17], 1u);
 				__syncthreads();
-				if (tid == 0) { sh.bufCount = level; sh.overflow = 0; }
+				// the redone pass re-merges the same id range: its two-match candidates must not be counted twice
+				if (tid == 0) { sh.bufCount = level; sh.nGe2 = levelGe2; sh.overflow = 0; }
 				__syncthreads();
 				if (level > k) { select_smallest<FS_THREADS>(sh, level, k); level = k; tauReal = true; }
 				safeMode = true;
@@ -695,6 +697,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_fast_search(IndexView ix, con
 			more = sh.lastPass == 0;
 			if (tid < MAX_QGRAMS && (uint32_t)tid < nLists) { sh.cur[tid] += sh.nTake[tid]; sh.rem[tid] -= sh.nTake[tid]; }
 			level = sh.bufCount;
+			levelGe2 = sh.nGe2;
 			const uint32_t nextLo = sh.passHi;
 			__syncthreads();
 			if (tid == 0) sh.passLo = nextLo;

@@ -68,12 +68,20 @@ struct DeviceIndex {
 	DevBuf<uint64_t> keyRow;     // [K] global first row of the key
 	DevBuf<uint64_t> keyHash;    // [K] 64-bit hash of the key string (shard-independent; multi-GPU merge identity)
 
+	// sieve: block bitmaps over the posting lists (sieve.cu). Derived from gramOff/postings, rebuilt after a load.
+	int sieveShift = 0;          // a block = 2^sieveShift consecutive term ids
+	uint32_t sieveWords = 0;     // 32-block words per bitmap (multiple of 8); 0 = the index has no sieve
+	uint32_t sieveSlots = 0;     // grams that have a bitmap
+	DevBuf<uint32_t> sieveSlot;  // [G] bitmap slot of the gram, 0xFFFFFFFF = none (short list)
+	DevBuf<uint32_t> sieveBits;  // [sieveSlots * sieveWords]
+	DevBuf<uint32_t> sieveCum;   // [sieveSlots * (sieveWords / 8 + 1)] absolute posting index at the start of every 8-word group
+
 	size_t device_bytes() const
 	{
 		return symTable.bytes() + validLut.bytes() + gramCodes.bytes() + gramOff.bytes() + postings.bytes() + termOff.bytes() +
 		       termChars.bytes() + termEdgeOff.bytes() + edgeKid.bytes() + edgeW.bytes() + shortTerms.bytes() + keyOff.bytes() +
 		       keyChars.bytes() + keyEdgeOff.bytes() + keyEdgeTerm.bytes() + keyEdgeW.bytes() + keyWmax.bytes() + keyRow.bytes() +
-		       keyHash.bytes();
+		       keyHash.bytes() + sieveSlot.bytes() + sieveBits.bytes() + sieveCum.bytes();
 	}
 };
 
@@ -108,7 +116,7 @@ struct PackedWords {
 };
 
 struct BuildStats {
-	double msTotal = 0, msH2D = 0, msIntern = 0, msEdges = 0, msGrams = 0, msD2H = 0;
+	double msTotal = 0, msH2D = 0, msIntern = 0, msEdges = 0, msGrams = 0, msSieve = 0, msD2H = 0;
 	uint64_t windows = 0;   // P' = gram windows before de-duplication
 	int hashRetries = 0;
 };
@@ -116,5 +124,8 @@ struct BuildStats {
 // Builds the device index from packed host words. Throws CudaError / std::runtime_error on failure.
 void build_index(DeviceIndex& ix, HostKeys& hk, const PackedWords& w, uint16_t rowSize, uint16_t gSize, int unitBytes,
                  uint64_t rowBase, const uint8_t validLut[256], cudaStream_t s, BuildStats* stats);
+
+// (Re)builds the sieve of an indexed DeviceIndex from its postings (sieve.cu).
+void build_sieve(DeviceIndex& ix, cudaStream_t s);
 
 }   // namespace ssb

@@ -19,6 +19,7 @@
 #include "textops.cuh"
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 
 namespace ssb {
 
@@ -56,6 +57,12 @@ struct IndexView {
 	const float* keyEdgeW;
 	const float* keyWmax;
 	const uint64_t* keyRow;
+	// sieve (block bitmaps, sieve.cu); sieveWords == 0: none
+	int sieveShift;
+	uint32_t sieveWords;
+	const uint32_t* sieveSlot;
+	const uint32_t* sieveBits;
+	const uint32_t* sieveCum;
 };
 
 IndexView make_view(const DeviceIndex& ix)
@@ -73,6 +80,8 @@ IndexView make_view(const DeviceIndex& ix)
 	v.keyOff = ix.keyOff.get(); v.keyChars = ix.keyChars.get();
 	v.keyEdgeOff = ix.keyEdgeOff.get(); v.keyEdgeTerm = ix.keyEdgeTerm.get(); v.keyEdgeW = ix.keyEdgeW.get();
 	v.keyWmax = ix.keyWmax.get(); v.keyRow = ix.keyRow.get();
+	v.sieveShift = ix.sieveShift; v.sieveWords = ix.sieveSlots ? ix.sieveWords : 0u;
+	v.sieveSlot = ix.sieveSlot.get(); v.sieveBits = ix.sieveBits.get(); v.sieveCum = ix.sieveCum.get();
 	return v;
 }
 
@@ -179,6 +188,7 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 	else cls = QC_DENSE;
 
 	uint32_t nLists = 0, total = 0;
+	bool sieveOk = false;
 	if (cls == QC_FAST || (cls == QC_DENSE && nGrams >= 1 && nGrams <= MAX_QGRAMS)) {
 		// lane i owns window i
 		const bool act = (uint32_t)lane < nGrams;
@@ -197,18 +207,22 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 		// duplicates: one list per distinct gram, multiplicity = number of windows (hpp:289-298 adds once per window)
 		unsigned peers = __match_any_sync(0xffffffffu, code);
 		const bool leader = act && code != ~0ull && (peers & ((1u << lane) - 1)) == 0;
-		uint32_t lo = 0, len = 0;
+		uint32_t lo = 0, len = 0, bm = 0xFFFFFFFFu;
 		if (leader) {
 			uint32_t a = 0, z = ix.G;
 			while (a < z) { uint32_t m = (a + z) >> 1; if (ix.gramCodes[m] < code) a = m + 1; else z = m; }
-			if (a < ix.G && ix.gramCodes[a] == code) { lo = ix.gramOff[a]; len = ix.gramOff[a + 1] - lo; }
+			if (a < ix.G && ix.gramCodes[a] == code) {
+				lo = ix.gramOff[a]; len = ix.gramOff[a + 1] - lo;
+				if (ix.sieveWords) bm = ix.sieveSlot[a];
+			}
 		}
 		unsigned found = __ballot_sync(0xffffffffu, leader && len > 0);
 		if (leader && len > 0) {
 			uint32_t slot = __popc(found & ((1u << lane) - 1));
-			d.listOff[slot] = lo; d.listLen[slot] = len; d.listMult[slot] = (uint8_t)__popc(peers);
+			d.listOff[slot] = lo; d.listLen[slot] = len; d.listMult[slot] = (uint8_t)__popc(peers); d.listSlot[slot] = bm;
 		}
 		nLists = __popc(found);
+		sieveOk = ix.sieveWords != 0 && nLists >= 1 && nLists <= SV_MAXL && !__any_sync(0xffffffffu, leader && len > 0 && bm == 0xFFFFFFFFu);
 		total = len;
 		for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
 	}
@@ -220,7 +234,7 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 			if ((double)s > 0.999) cprom = c;                                         // hpp:328
 		}
 		d.cls = cls; d.qlen = qlen; d.nGrams = nGrams; d.nLists = nLists; d.cmin = cmin; d.cprom = cprom; d.total = total; d.qbeg = b;
-		d.flags = (shortActive ? 1u : 0u) | ((shortActive && qlen <= g) ? 2u : 0u);
+		d.flags = (shortActive ? 1u : 0u) | ((shortActive && qlen <= g) ? 2u : 0u) | ((sieveOk && !shortActive && cls == QC_FAST) ? 4u : 0u);
 		outCount[q] = 0;
 		if (cls == QC_FAST) fastList[atomicAdd(&counters[0], 1u)] = q;
 		else if (cls == QC_DENSE || cls == QC_WILDCARD) denseList[atomicAdd(&counters[1], 1u)] = q;
@@ -230,7 +244,7 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 }   // namespace
 
 #include "fast_path.cuh"   // k_fast_search (inside namespace ssb)
-#include "hash_path.cuh"   // k_hash_search
+#include "sieve_path.cuh"  // k_sieve_search
 
 namespace {
 
@@ -557,30 +571,62 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	// list of their own behind the candidate buffer instead of the small one that aliases the select histogram
 	const uint32_t defExt = (ix.identity && ix.uniformW) ? 0u : (uint32_t)FS_DEF_EXT;
 	const size_t smemBytes = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)bufCap * 8 + (size_t)defExt * 8;
-	static int numSMs = 0;
-	static int ctasFor[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	// per-device launch configuration, set up once and safely under concurrent searches on different indexes (only the index's
+	// own mutex is held here): shared-memory opt-in of every kernel variant first, occupancy per configuration on demand
+	struct LaunchCfg {
+		std::once_flag once;
+		std::mutex mu;
+		int numSMs = 0;
+		int ctasFor[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+		int sieveCtas[6] = {0, 0, 0, 0, 0, 0};
+	};
+	static LaunchCfg cfgOf[64];
+	int dev = 0;
+	SSB_CUDA(cudaGetDevice(&dev));
+	LaunchCfg& lc = cfgOf[dev & 63];
 	const bool withShort = ix.nShort > 0;
-	const int cfg = (bufCap == 1024 ? 0 : (bufCap == 2048 ? 1 : 2)) + (withShort ? 3 : 0) + (defExt ? 6 : 0);
-	if (!numSMs) {
-		int dev = 0;
-		SSB_CUDA(cudaGetDevice(&dev));
-		SSB_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
+	const int bufIdx = bufCap == 1024 ? 0 : (bufCap == 2048 ? 1 : 2);
+	const int cfg = bufIdx + (withShort ? 3 : 0) + (defExt ? 6 : 0);
+	const size_t svBytes = ((sizeof(SieveShared) + 15) & ~size_t(15)) + (size_t)bufCap * 8 + (size_t)defExt * 8;
+	std::call_once(lc.once, [&] {
+		int n = 0;
+		SSB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
 		const int maxSmem = (int)(((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)FS_BUF_MAX * 8 + (size_t)FS_DEF_EXT * 8);
 		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
 		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
 		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
 		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+		const int maxSv = (int)(((sizeof(SieveShared) + 15) & ~size_t(15)) + (size_t)FS_BUF_MAX * 8 + (size_t)FS_DEF_EXT * 8);
+		SSB_CUDA(cudaFuncSetAttribute(k_sieve_search<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSv));
+		SSB_CUDA(cudaFuncSetAttribute(k_sieve_search<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSv));
 		SSB_CUDA(cudaFuncSetAttribute(k_order_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ORDER_MAX * 8)));
+		lc.numSMs = n;
+	});
+	const int numSMs = lc.numSMs;
+	int ctasPerSM, sieveCtasPerSM;
+	{
+		std::lock_guard<std::mutex> lk(lc.mu);
+		if (!lc.ctasFor[cfg]) {
+			int c = 0;
+			if (withShort) SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_fast_search<U, true>, FS_THREADS, smemBytes));
+			else SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_fast_search<U, false>, FS_THREADS, smemBytes));
+			lc.ctasFor[cfg] = std::max(c, 1);
+			if (getenv("SSB_DEBUG"))
+				fprintf(stderr, "[ssb] k_fast_search: sizeof(FastShared)=%zu, bufCap=%u, dynamic smem=%zu B, %d CTAs/SM x %d threads (short-term variant: %d)\n",
+				        sizeof(FastShared), bufCap, smemBytes, lc.ctasFor[cfg], FS_THREADS, (int)withShort);
+		}
+		const int scfg = bufIdx + (defExt ? 3 : 0);
+		if (!lc.sieveCtas[scfg]) {
+			int c = 0;
+			SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_sieve_search<U>, SV_THREADS, svBytes));
+			lc.sieveCtas[scfg] = std::max(c, 1);
+			if (getenv("SSB_DEBUG"))
+				fprintf(stderr, "[ssb] k_sieve_search: sizeof(SieveShared)=%zu, dynamic smem=%zu B, %d CTAs/SM x %d threads\n", sizeof(SieveShared),
+				        svBytes, lc.sieveCtas[scfg], SV_THREADS);
+		}
+		ctasPerSM = lc.ctasFor[cfg];
+		sieveCtasPerSM = lc.sieveCtas[scfg];
 	}
-	if (!ctasFor[cfg]) {
-		if (withShort) SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasFor[cfg], k_fast_search<U, true>, FS_THREADS, smemBytes));
-		else SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasFor[cfg], k_fast_search<U, false>, FS_THREADS, smemBytes));
-		if (ctasFor[cfg] < 1) ctasFor[cfg] = 1;
-		if (getenv("SSB_DEBUG"))
-			fprintf(stderr, "[ssb] k_fast_search: sizeof(FastShared)=%zu, bufCap=%u, dynamic smem=%zu B, %d CTAs/SM x %d threads (short-term variant: %d)\n",
-			        sizeof(FastShared), bufCap, smemBytes, ctasFor[cfg], FS_THREADS, (int)withShort);
-	}
-	const int ctasPerSM = ctasFor[cfg];
 	unsigned long long* statCounters = reinterpret_cast<unsigned long long*>(ws.counters.get() + 8);
 	// tiny batch with pinned result arrays: see k_finalize_tiny (no events: nobody profiles a single query through them)
 	const bool tiny = hr && ix.K && nq <= 32 && hr->capQ >= nq && hr->capResults >= (size_t)nq * stride;
@@ -597,41 +643,29 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		SSB_LAUNCH_CHECK();
 	}
 	if (!tiny) SSB_CUDA(cudaEventRecord(ws.ev1, s));
-	// persistent grids: one wave of resident CTAs, queries handed out by an atomic cursor. k_hash_search takes the fast queries
-	// first (limit <= 512) and hands the ones it cannot answer to k_fast_search through fastList2.
-	// Which kernel first? Measured (scripts/probe_configs.py, 4096 queries, ms per batch, merge vs hash): C4 headline 1.09 vs
-	// 1.88; C4 with threshold 0.3: 0.88 vs 1.10; C2 (descriptions + weights, threshold 0.3): 0.67 vs 0.97; C3 (wide): 0.03 vs
-	// 0.08. The register merge wins everywhere, so k_hash_search runs only on request (ssb_set_search_path / SSB_HASH).
-	static const int envPath = getenv("SSB_HASH") ? 1 : 0;
+	// persistent grids: one wave of resident CTAs, queries handed out by an atomic cursor. k_sieve_search goes through the fast
+	// queries first and hands the ones it does not take (a list without bitmap, > 16 lists, edit-distance path) or cannot finish
+	// to k_fast_search through fastList2. ssb_set_search_path(0) / SSB_MERGE=1: k_fast_search answers everything (the parity tests
+	// run every batch both ways).
+	static const int envPath = getenv("SSB_MERGE") ? 0 : 1;
 	int pathOpt = g_search_path.load(std::memory_order_relaxed);
 	if (pathOpt < 0) pathOpt = envPath;
-	const bool useHash = pathOpt == 1 && limit <= (uint32_t)HS_KLIM;
-	if (useHash) {
-		static int hashCtas = 0;
-		const size_t hsBytes = ((sizeof(HashShared) + 15) & ~size_t(15)) + (size_t)1024 * 8;
-		if (!hashCtas) {
-			SSB_CUDA(cudaFuncSetAttribute(k_hash_search<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsBytes));
-			SSB_CUDA(cudaFuncSetAttribute(k_hash_search<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsBytes));
-			SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hashCtas, k_hash_search<U>, HS_THREADS, hsBytes));
-			if (hashCtas < 1) hashCtas = 1;
-			if (getenv("SSB_DEBUG"))
-				fprintf(stderr, "[ssb] k_hash_search: sizeof(HashShared)=%zu, dynamic smem=%zu B, %d CTAs/SM x %d threads\n",
-				        sizeof(HashShared), hsBytes, hashCtas, HS_THREADS);
-		}
-		const unsigned hgrid = (unsigned)std::min<size_t>((size_t)numSMs * hashCtas, std::max<uint32_t>(nq, 1));
-		k_hash_search<U><<<hgrid, HS_THREADS, hsBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(), ws.fastList2.get(),
-		                                                    limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(),
-		                                                    statCounters, 1024u, threshold);
-		SSB_LAUNCH_CHECK();
-	}
+	const bool useSieve = pathOpt == 1 && v.sieveWords != 0;
 	// direct delivery (see HostOut): possible when the caller gave pinned CSR arrays, the stride is the limit itself and only
 	// k_fast_search writes results; it holds if every query turns out to fill its `limit` slots (checked after the kernel)
-	const bool direct = !tiny && !useHash && hr && ix.K && hr->capQ >= nq && hr->capResults >= (size_t)nq * stride && stride == limit &&
+	const bool direct = !tiny && hr && ix.K && hr->capQ >= nq && hr->capResults >= (size_t)nq * stride && stride == limit &&
 	                    (size_t)nq * stride < (1ull << 32);
 	HostOut ho{};
 	if (direct) { ho.kids = hr->kids; ho.scores = hr->scores; ho.rows = hr->rows; ho.strs = reinterpret_cast<uint64_t*>(hr->strs); ho.strBase = hr->strBase; }
-	const uint32_t* fl = useHash ? ws.fastList2.get() : ws.fastList.get();
-	const uint32_t nIdx = useHash ? 5u : 0u, curIdx = useHash ? 12u : 2u;
+	if (useSieve) {
+		const unsigned sgrid = (unsigned)std::min<size_t>((size_t)numSMs * sieveCtasPerSM, std::max<uint32_t>(nq, 1));
+		k_sieve_search<U><<<sgrid, SV_THREADS, svBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(), ws.fastList2.get(),
+		                                                    limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(),
+		                                                    statCounters, bufCap, threshold, defExt, ho);
+		SSB_LAUNCH_CHECK();
+	}
+	const uint32_t* fl = useSieve ? ws.fastList2.get() : ws.fastList.get();
+	const uint32_t nIdx = useSieve ? 5u : 0u, curIdx = useSieve ? 12u : 2u;
 	const unsigned grid = (unsigned)std::min<size_t>((size_t)numSMs * ctasPerSM, std::max<uint32_t>(nq, 1));
 	if (withShort)
 		k_fast_search<U, true><<<grid, FS_THREADS, smemBytes, s>>>(v, ws.desc.get(), qn, fl, ws.counters.get(),
@@ -718,12 +752,14 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	}
 	if (st) {
 		st->nFast = nFast; st->nDense = nDense; st->nOverflow = nOverflow;
-		st->nHash = hc[6]; st->nHashHandover = hc[5]; st->nHashGiveUp = hc[7];
+		st->nSieve = hc[6]; st->nSieveHandover = hc[5]; st->nSieveGiveUp = hc[28];
 		static const bool dbg = getenv("SSB_DEBUG") != nullptr;
 		if (dbg && nFast)
 			fprintf(stderr, "[ssb] k_fast_search per query: %.1f passes, %.2f redone, %.1f selects, %.1f deferred evaluations\n", hc[16] / (double)nFast,
 			        hc[17] / (double)nFast, hc[18] / (double)nFast, hc[19] / (double)nFast);
-		if (hc[7] && dbg) fprintf(stderr, "[ssb] k_hash_search gave up on %u queries: buffer %u, queue %u, other %u\n", hc[7], hc[13], hc[14], hc[15]);
+		if (dbg && hc[6])
+			fprintf(stderr, "[ssb] k_sieve_search per query: %.1f passes (%.2f redone), %.0f candidate blocks, %.0f probes; gave up on %u\n",
+			        hc[24] / (double)hc[6], hc[27] / (double)hc[6], hc[26] / (double)hc[6], hc[25] / (double)hc[6], hc[28]);
 		st->postingsTouched = postings;
 		st->msDevice = st->msFastKernel = 0;
 		if (!tiny) {

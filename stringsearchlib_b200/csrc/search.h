@@ -8,6 +8,7 @@ namespace ssb {
 
 constexpr int MAX_QGRAMS = 32;      // fast path: at most 32 gram windows per query (longer queries take the dense path)
 constexpr int FAST_KLIM = 2048;     // fast path: limit <= FAST_KLIM
+constexpr int SV_MAXL = 16;         // k_sieve_search: at most 16 posting lists per query
 
 enum QueryClass : uint32_t { QC_EMPTY = 0, QC_FAST = 1, QC_DENSE = 2, QC_WILDCARD = 3 };
 
@@ -21,17 +22,19 @@ struct QDesc {
 	uint32_t cprom;       // smallest count c with (double)((float)c / (float)nGrams) > 0.999 (hpp:328)
 	uint32_t total;       // postings over all lists
 	uint32_t qbeg;        // offset of the normalised query in the qnorm buffer (units)
-	uint32_t flags;       // bit 0: the short (edit-distance) path runs (hpp:381); bit 1: it also scans every long term (hpp:247)
+	uint32_t flags;       // bit 0: the short (edit-distance) path runs (hpp:381); bit 1: it also scans every long term (hpp:247);
+	                      // bit 2: k_sieve_search can take the query (every list has a block bitmap)
 	uint32_t pad;
 	uint32_t listOff[MAX_QGRAMS];
 	uint32_t listLen[MAX_QGRAMS];
+	uint32_t listSlot[MAX_QGRAMS];   // bitmap slot of the list's gram (DeviceIndex::sieveSlot), 0xFFFFFFFF = none
 	uint64_t qcode[MAX_QGRAMS];   // code of every window (dups kept); ~0 = contains a symbol absent from the index
 	uint8_t listMult[MAX_QGRAMS];
 };
 
 struct SearchStats {
 	uint32_t nFast = 0, nDense = 0, nWildcard = 0, nEmpty = 0, nOverflow = 0;
-	uint32_t nHash = 0, nHashHandover = 0, nHashGiveUp = 0;   // k_hash_search: answered / handed to k_fast_search / of those, given up mid-query
+	uint32_t nSieve = 0, nSieveHandover = 0, nSieveGiveUp = 0;   // k_sieve_search: answered / handed to k_fast_search / of those, given up mid-query
 	uint64_t postingsTouched = 0;   // sum over fast queries of posting-list lengths (algorithmic bytes / 4)
 	uint64_t candidates = 0;
 	float msDevice = 0;             // CUDA-event time of the device part of the last batch
@@ -44,9 +47,10 @@ struct SearchWorkspace {
 	DevBuf<uint8_t> qchars, qnorm;
 	DevBuf<uint32_t> qoff;
 	DevBuf<QDesc> desc;
-	DevBuf<uint32_t> fastList, fastList2, denseList;   // fastList2: queries k_hash_search hands to k_fast_search
+	DevBuf<uint32_t> fastList, fastList2, denseList;   // fastList2: queries k_sieve_search hands to k_fast_search
 	// [0]=nFast [1]=nDense [2]=work cursor [3]=overflow count [4]=any out-of-band list [5]=handed to k_fast_search
-	// [6]=answered by k_hash_search [7]=of [5], given up mid-query [12]=k_fast_search cursor; [8..11] = two u64 statistics
+	// [6]=answered by k_sieve_search [28]=of [5], given up mid-query [12]=k_fast_search cursor; [8..11] = two u64 statistics;
+	// [16..19] k_fast_search and [24..27] k_sieve_search per-pass statistics (SSB_DEBUG)
 	// (postings touched, spare). One memset per batch, one async D2H into pinned hostCounters.
 	DevBuf<uint32_t> counters;
 	PinBuf<uint32_t> hostCounters;

@@ -1,0 +1,128 @@
+// sieve.cu — block bitmaps over the posting lists (the "sieve" that k_sieve_search reads instead of the postings).
+//
+// The reference counts matches by touching every posting of every query gram (nGramSearch.hpp:289-298). Once the running
+// k-th best or the threshold (hpp:313-316) demands c matches, a term can only matter if it lies in a BLOCK of 2^shift
+// consecutive term ids in which at least c of the query's lists have a posting. For every gram with a long enough list
+// this file derives from the (bit-exact) CSR postings
+//   sieveBits[slot]  one bit per block: the list has a posting in the block             (W 32-bit words, W % 8 == 0)
+//   sieveCum[slot]   per group of 8 words (256 blocks): absolute index of the list's first posting at or after the group
+// so that a query streams K bitmaps (K * T / 2^shift / 8 bytes) through a bit-sliced threshold counter and only reads the
+// postings of the few blocks that pass it (rank inside the group = popcount of the lower bits). Derived data: rebuilt
+// after ssb_index_load, never serialised, never compared by the parity tests — postings stay the source of truth.
+#include "index.h"
+#include "primitives.cuh"
+#include <algorithm>
+#include <cmath>
+
+namespace ssb {
+namespace {
+
+constexpr int TPB = 256;
+inline unsigned grid_for(size_t n, int tpb = TPB) { return (unsigned)std::max<size_t>(1, (n + tpb - 1) / tpb); }
+
+// [0] = sum of list lengths, [1] = sum of squared list lengths (query grams are drawn roughly in proportion to their
+// frequency, so the length a query sees is the P-weighted mean sum(L^2) / sum(L))
+__global__ void __launch_bounds__(TPB) k_sieve_stats(const uint32_t* __restrict__ gramOff, uint32_t G, unsigned long long* __restrict__ acc)
+{
+	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long l = 0, l2 = 0;
+	if (g < G) { l = gramOff[g + 1] - gramOff[g]; l2 = l * l; }
+	for (int o = 16; o; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); l2 += __shfl_xor_sync(0xffffffffu, l2, o); }
+	if ((threadIdx.x & 31) == 0 && l) { atomicAdd(&acc[0], l); atomicAdd(&acc[1], l2); }
+}
+
+__global__ void __launch_bounds__(TPB) k_sieve_flags(const uint32_t* __restrict__ gramOff, uint32_t G, uint32_t minLen, uint8_t* __restrict__ flag)
+{
+	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g < G) flag[g] = (gramOff[g + 1] - gramOff[g]) >= minLen;
+}
+
+__global__ void __launch_bounds__(TPB) k_sieve_slots(const uint8_t* __restrict__ flag, const uint32_t* __restrict__ pos, uint32_t G,
+                                                     uint32_t* __restrict__ slotOf, uint32_t* __restrict__ gramOfSlot)
+{
+	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= G) return;
+	if (flag[g]) { slotOf[g] = pos[g]; gramOfSlot[pos[g]] = g; }
+	else slotOf[g] = 0xFFFFFFFFu;
+}
+
+// one CTA per slot: bits from the postings, group directory by binary search
+__global__ void __launch_bounds__(TPB) k_sieve_fill(const uint32_t* __restrict__ gramOfSlot, const uint32_t* __restrict__ gramOff,
+                                                    const uint32_t* __restrict__ postings, int shift, uint32_t W,
+                                                    uint32_t* __restrict__ bits, uint32_t* __restrict__ cum)
+{
+	const uint32_t slot = blockIdx.x;
+	const uint32_t g = gramOfSlot[slot];
+	const uint32_t lo = gramOff[g], hi = gramOff[g + 1];
+	uint32_t* myBits = bits + (size_t)slot * W;
+	for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+		const uint32_t b = postings[i] >> shift;
+		atomicOr(&myBits[b >> 5], 1u << (b & 31));
+	}
+	const uint32_t nGroups = W >> 3;
+	uint32_t* myCum = cum + (size_t)slot * (nGroups + 1);
+	for (uint32_t gr = threadIdx.x; gr <= nGroups; gr += blockDim.x) {
+		// first posting whose block is >= 256 * gr
+		const unsigned long long firstId = ((unsigned long long)gr << 8) << shift;
+		uint32_t a = lo, z = hi;
+		while (a < z) {
+			const uint32_t m = a + ((z - a) >> 1);
+			if ((unsigned long long)postings[m] < firstId) a = m + 1; else z = m;
+		}
+		myCum[gr] = a;
+	}
+}
+
+}   // namespace
+
+void build_sieve(DeviceIndex& ix, cudaStream_t s)
+{
+	ix.sieveShift = 0; ix.sieveWords = 0; ix.sieveSlots = 0;
+	ix.sieveSlot.release(); ix.sieveBits.release(); ix.sieveCum.release();
+	static const bool off = getenv("SSB_NO_SIEVE") != nullptr;
+	if (off || !ix.indexed || ix.G == 0 || ix.P == 0 || ix.T == 0) return;
+
+	DevBuf<unsigned long long> acc(2, s);
+	acc.zero(s);
+	k_sieve_stats<<<grid_for(ix.G), TPB, 0, s>>>(ix.gramOff.get(), ix.G, acc.get());
+	SSB_LAUNCH_CHECK();
+	unsigned long long h[2] = {0, 0};
+	SSB_CUDA(cudaMemcpyAsync(h, acc.get(), sizeof h, cudaMemcpyDeviceToHost, s));
+	SSB_CUDA(cudaStreamSynchronize(s));
+	if (h[0] == 0) return;
+	const double lw = (double)h[1] / (double)h[0];          // posting-weighted mean list length
+	// block size: the typical list sets about one bit in 32 (then "c of K lists hit the block" is rare for c >= 2 while a
+	// bitmap costs about as many bytes as the list it summarises)
+	int shift = (int)std::lround(std::log2(std::max(1.0, (double)ix.T / (32.0 * lw))));
+	if (const char* e = getenv("SSB_SIEVE_SHIFT")) shift = atoi(e);
+	shift = std::max(0, std::min(shift, 20));
+	const uint64_t nBlocks = (((uint64_t)ix.T - 1) >> shift) + 1;
+	const uint64_t W = (((nBlocks + 31) / 32) + 7) & ~uint64_t(7);
+	// a gram gets a bitmap when the bitmap is at most twice as large as its posting list — or always, on indexes so small
+	// that bitmaps for every gram stay within that budget overall
+	uint32_t minLen = (uint32_t)std::max<uint64_t>(1, W / 2);
+	if ((uint64_t)ix.G * W <= 2ull * ix.P + (1u << 18)) minLen = 1;
+
+	DevBuf<uint8_t> flag(ix.G, s);
+	DevBuf<uint32_t> pos(ix.G, s), dN(1, s);
+	k_sieve_flags<<<grid_for(ix.G), TPB, 0, s>>>(ix.gramOff.get(), ix.G, minLen, flag.get());
+	SSB_LAUNCH_CHECK();
+	exclusive_scan_u8_u32(flag.get(), pos.get(), ix.G, dN.get(), s);
+	uint32_t nSlots = 0;
+	SSB_CUDA(cudaMemcpyAsync(&nSlots, dN.get(), 4, cudaMemcpyDeviceToHost, s));
+	SSB_CUDA(cudaStreamSynchronize(s));
+	if (nSlots == 0) return;
+	DevBuf<uint32_t> gramOfSlot(nSlots, s);
+	ix.sieveSlot.alloc(ix.G, s);
+	k_sieve_slots<<<grid_for(ix.G), TPB, 0, s>>>(flag.get(), pos.get(), ix.G, ix.sieveSlot.get(), gramOfSlot.get());
+	SSB_LAUNCH_CHECK();
+	ix.sieveBits.alloc((size_t)nSlots * W, s);
+	ix.sieveBits.zero(s);
+	ix.sieveCum.alloc((size_t)nSlots * (W / 8 + 1), s);
+	k_sieve_fill<<<nSlots, TPB, 0, s>>>(gramOfSlot.get(), ix.gramOff.get(), ix.postings.get(), shift, (uint32_t)W, ix.sieveBits.get(),
+	                                    ix.sieveCum.get());
+	SSB_LAUNCH_CHECK();
+	ix.sieveShift = shift; ix.sieveWords = (uint32_t)W; ix.sieveSlots = nSlots;      // (scratch buffers are freed in stream order)
+}
+
+}   // namespace ssb

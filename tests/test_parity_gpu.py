@@ -55,7 +55,7 @@ def check_tables(ix, S):
 
 
 def check_search(ix, S, queries, threshold, limit, o=None):
-    """every batch is answered twice — k_fast_search first (path 0, the default) and k_hash_search first (path 1) — and
+    """every batch is answered twice — k_sieve_search first (path 1, the default) and k_fast_search alone (path 0) — and
     both must equal the oracle bit for bit"""
     import stringsearchlib_b200 as m
     o = o or S.tables()
@@ -471,17 +471,19 @@ def test_properties_full_size(ssb):
         same = sc[:, :-1] == sc[:, 1:]
         assert np.all(kid[:, :-1][same] < kid[:, 1:][same])          # ties: kid ascending
         ms, msk, st = ix.search_resident(nq, 0.0, 100)
-        assert st["nFast"] == nq and st["nDense"] == 0 and st["nOverflow"] == 0 and st["nHash"] == 0
-        # the other fast kernel (k_hash_search first) must answer the batch identically, and answer most of it itself
+        # the default path: k_sieve_search answers (nearly) everything itself
+        assert st["nFast"] == nq and st["nDense"] == 0 and st["nOverflow"] == 0, st
+        assert st["nSieve"] + st["nSieveHandover"] == nq and st["nSieve"] > nq // 2, st
+        # k_fast_search alone (the register merge) must answer the batch identically
         try:
-            ssb.set_search_path(1)
+            ssb.set_search_path(0)
             r3 = ix.search_batch(q, 0.0, 100)
             _, _, st3 = ix.search_resident(nq, 0.0, 100)
         finally:
             ssb.set_search_path(-1)
         assert np.array_equal(r1.offsets, r3.offsets) and np.array_equal(r1.kids, r3.kids)
         assert np.array_equal(r1.scores.view(np.uint32), r3.scores.view(np.uint32))
-        assert st3["nHash"] + st3["nHashHandover"] == nq and st3["nHash"] > nq // 2 and st3["nDense"] == 0, st3
+        assert st3["nSieve"] == 0 and st3["nFast"] == nq and st3["nDense"] == 0, st3
         exact = ix.search_batch(keys.slice(1000, 1064), 0.0, 5, strings=True)
         for i in range(64):
             assert exact.query(i)[3][0] == keys.get(1000 + i)
