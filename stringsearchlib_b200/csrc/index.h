@@ -16,6 +16,7 @@
 namespace ssb {
 
 constexpr int MAX_GSIZE = 8;
+constexpr uint32_t SIEVE_GROUP_BLOCKS = 96;   // blocks per 16-byte sieve group (sieve.cu)
 
 struct DeviceIndex {
 	// configuration
@@ -70,18 +71,17 @@ struct DeviceIndex {
 
 	// sieve: block bitmaps over the posting lists (sieve.cu). Derived from gramOff/postings, rebuilt after a load.
 	int sieveShift = 0;          // a block = 2^sieveShift consecutive term ids
-	uint32_t sieveWords = 0;     // 32-block words per bitmap (multiple of 8); 0 = the index has no sieve
+	uint32_t sieveNGroups = 0;   // 96-block groups per bitmap; 0 = the index has no sieve
 	uint32_t sieveSlots = 0;     // grams that have a bitmap
 	DevBuf<uint32_t> sieveSlot;  // [G] bitmap slot of the gram, 0xFFFFFFFF = none (short list)
-	DevBuf<uint32_t> sieveBits;  // [sieveSlots * sieveWords]
-	DevBuf<uint32_t> sieveCum;   // [sieveSlots * (sieveWords / 8 + 1)] absolute posting index at the start of every 8-word group
+	DevBuf<uint32_t> sieveGroups;// [sieveSlots * sieveNGroups * 4] per group { first posting index, 3 x 32 block bits }
 
 	size_t device_bytes() const
 	{
 		return symTable.bytes() + validLut.bytes() + gramCodes.bytes() + gramOff.bytes() + postings.bytes() + termOff.bytes() +
 		       termChars.bytes() + termEdgeOff.bytes() + edgeKid.bytes() + edgeW.bytes() + shortTerms.bytes() + keyOff.bytes() +
 		       keyChars.bytes() + keyEdgeOff.bytes() + keyEdgeTerm.bytes() + keyEdgeW.bytes() + keyWmax.bytes() + keyRow.bytes() +
-		       keyHash.bytes() + sieveSlot.bytes() + sieveBits.bytes() + sieveCum.bytes();
+		       keyHash.bytes() + sieveSlot.bytes() + sieveGroups.bytes();
 	}
 };
 

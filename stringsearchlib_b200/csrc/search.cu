@@ -57,12 +57,11 @@ struct IndexView {
 	const float* keyEdgeW;
 	const float* keyWmax;
 	const uint64_t* keyRow;
-	// sieve (block bitmaps, sieve.cu); sieveWords == 0: none
+	// sieve (block bitmaps, sieve.cu); sieveNGroups == 0: none
 	int sieveShift;
-	uint32_t sieveWords;
+	uint32_t sieveNGroups;
 	const uint32_t* sieveSlot;
-	const uint32_t* sieveBits;
-	const uint32_t* sieveCum;
+	const uint4* sieveGroups;
 };
 
 IndexView make_view(const DeviceIndex& ix)
@@ -80,8 +79,8 @@ IndexView make_view(const DeviceIndex& ix)
 	v.keyOff = ix.keyOff.get(); v.keyChars = ix.keyChars.get();
 	v.keyEdgeOff = ix.keyEdgeOff.get(); v.keyEdgeTerm = ix.keyEdgeTerm.get(); v.keyEdgeW = ix.keyEdgeW.get();
 	v.keyWmax = ix.keyWmax.get(); v.keyRow = ix.keyRow.get();
-	v.sieveShift = ix.sieveShift; v.sieveWords = ix.sieveSlots ? ix.sieveWords : 0u;
-	v.sieveSlot = ix.sieveSlot.get(); v.sieveBits = ix.sieveBits.get(); v.sieveCum = ix.sieveCum.get();
+	v.sieveShift = ix.sieveShift; v.sieveNGroups = ix.sieveSlots ? ix.sieveNGroups : 0u;
+	v.sieveSlot = ix.sieveSlot.get(); v.sieveGroups = reinterpret_cast<const uint4*>(ix.sieveGroups.get());
 	return v;
 }
 
@@ -213,7 +212,7 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 			while (a < z) { uint32_t m = (a + z) >> 1; if (ix.gramCodes[m] < code) a = m + 1; else z = m; }
 			if (a < ix.G && ix.gramCodes[a] == code) {
 				lo = ix.gramOff[a]; len = ix.gramOff[a + 1] - lo;
-				if (ix.sieveWords) bm = ix.sieveSlot[a];
+				if (ix.sieveNGroups) bm = ix.sieveSlot[a];
 			}
 		}
 		unsigned found = __ballot_sync(0xffffffffu, leader && len > 0);
@@ -222,7 +221,7 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 			d.listOff[slot] = lo; d.listLen[slot] = len; d.listMult[slot] = (uint8_t)__popc(peers); d.listSlot[slot] = bm;
 		}
 		nLists = __popc(found);
-		sieveOk = ix.sieveWords != 0 && nLists >= 1 && nLists <= SV_MAXL && !__any_sync(0xffffffffu, leader && len > 0 && bm == 0xFFFFFFFFu);
+		sieveOk = ix.sieveNGroups != 0 && nLists >= 1 && nLists <= SV_MAXL && !__any_sync(0xffffffffu, leader && len > 0 && bm == 0xFFFFFFFFu);
 		total = len;
 		for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
 	}
@@ -650,7 +649,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	static const int envPath = getenv("SSB_MERGE") ? 0 : 1;
 	int pathOpt = g_search_path.load(std::memory_order_relaxed);
 	if (pathOpt < 0) pathOpt = envPath;
-	const bool useSieve = pathOpt == 1 && v.sieveWords != 0;
+	const bool useSieve = pathOpt == 1 && v.sieveNGroups != 0;
 	// direct delivery (see HostOut): possible when the caller gave pinned CSR arrays, the stride is the limit itself and only
 	// k_fast_search writes results; it holds if every query turns out to fill its `limit` slots (checked after the kernel)
 	const bool direct = !tiny && hr && ix.K && hr->capQ >= nq && hr->capResults >= (size_t)nq * stride && stride == limit &&

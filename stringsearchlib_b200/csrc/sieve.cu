@@ -3,12 +3,13 @@
 // The reference counts matches by touching every posting of every query gram (nGramSearch.hpp:289-298). Once the running
 // k-th best or the threshold (hpp:313-316) demands c matches, a term can only matter if it lies in a BLOCK of 2^shift
 // consecutive term ids in which at least c of the query's lists have a posting. For every gram with a long enough list
-// this file derives from the (bit-exact) CSR postings
-//   sieveBits[slot]  one bit per block: the list has a posting in the block             (W 32-bit words, W % 8 == 0)
-//   sieveCum[slot]   per group of 8 words (256 blocks): absolute index of the list's first posting at or after the group
-// so that a query streams K bitmaps (K * T / 2^shift / 8 bytes) through a bit-sliced threshold counter and only reads the
-// postings of the few blocks that pass it (rank inside the group = popcount of the lower bits). Derived data: rebuilt
-// after ssb_index_load, never serialised, never compared by the parity tests — postings stay the source of truth.
+// this file derives from the (bit-exact) CSR postings one array of 16-byte GROUPS, 96 blocks each:
+//   { first, bits0, bits1, bits2 }   first = absolute index of the list's first posting at or after the group's first block,
+//                                    bits  = one bit per block: the list has a posting in the block
+// so that a query streams K such arrays (K * T / 2^shift / 6 bytes) through a bit-sliced threshold counter and only reads
+// the postings of the few blocks that pass it: first + popcount of the lower bits of the same 16 bytes is the position of the
+// block's first posting. Derived data: rebuilt after ssb_index_load, never serialised, never compared by the parity tests —
+// postings stay the source of truth.
 #include "index.h"
 #include "primitives.cuh"
 #include <algorithm>
@@ -46,30 +47,28 @@ __global__ void __launch_bounds__(TPB) k_sieve_slots(const uint8_t* __restrict__
 	else slotOf[g] = 0xFFFFFFFFu;
 }
 
-// one CTA per slot: bits from the postings, group directory by binary search
+// one CTA per slot: bits from the postings, the groups' first-posting entries by binary search
 __global__ void __launch_bounds__(TPB) k_sieve_fill(const uint32_t* __restrict__ gramOfSlot, const uint32_t* __restrict__ gramOff,
-                                                    const uint32_t* __restrict__ postings, int shift, uint32_t W,
-                                                    uint32_t* __restrict__ bits, uint32_t* __restrict__ cum)
+                                                    const uint32_t* __restrict__ postings, int shift, uint32_t nGroups,
+                                                    uint32_t* __restrict__ groups)
 {
 	const uint32_t slot = blockIdx.x;
 	const uint32_t g = gramOfSlot[slot];
 	const uint32_t lo = gramOff[g], hi = gramOff[g + 1];
-	uint32_t* myBits = bits + (size_t)slot * W;
+	uint32_t* mine = groups + (size_t)slot * nGroups * 4;
 	for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
 		const uint32_t b = postings[i] >> shift;
-		atomicOr(&myBits[b >> 5], 1u << (b & 31));
+		const uint32_t v = b >> 5, gr = v / 3u, k = v - 3u * gr;            // virtual word v = 3 * group + k
+		atomicOr(&mine[(size_t)gr * 4 + 1 + k], 1u << (b & 31));
 	}
-	const uint32_t nGroups = W >> 3;
-	uint32_t* myCum = cum + (size_t)slot * (nGroups + 1);
-	for (uint32_t gr = threadIdx.x; gr <= nGroups; gr += blockDim.x) {
-		// first posting whose block is >= 256 * gr
-		const unsigned long long firstId = ((unsigned long long)gr << 8) << shift;
+	for (uint32_t gr = threadIdx.x; gr < nGroups; gr += blockDim.x) {
+		const unsigned long long firstId = ((unsigned long long)gr * SIEVE_GROUP_BLOCKS) << shift;
 		uint32_t a = lo, z = hi;
 		while (a < z) {
 			const uint32_t m = a + ((z - a) >> 1);
 			if ((unsigned long long)postings[m] < firstId) a = m + 1; else z = m;
 		}
-		myCum[gr] = a;
+		mine[(size_t)gr * 4] = a;
 	}
 }
 
@@ -77,8 +76,8 @@ __global__ void __launch_bounds__(TPB) k_sieve_fill(const uint32_t* __restrict__
 
 void build_sieve(DeviceIndex& ix, cudaStream_t s)
 {
-	ix.sieveShift = 0; ix.sieveWords = 0; ix.sieveSlots = 0;
-	ix.sieveSlot.release(); ix.sieveBits.release(); ix.sieveCum.release();
+	ix.sieveShift = 0; ix.sieveNGroups = 0; ix.sieveSlots = 0;
+	ix.sieveSlot.release(); ix.sieveGroups.release();
 	static const bool off = getenv("SSB_NO_SIEVE") != nullptr;
 	if (off || !ix.indexed || ix.G == 0 || ix.P == 0 || ix.T == 0) return;
 
@@ -97,11 +96,11 @@ void build_sieve(DeviceIndex& ix, cudaStream_t s)
 	if (const char* e = getenv("SSB_SIEVE_SHIFT")) shift = atoi(e);
 	shift = std::max(0, std::min(shift, 20));
 	const uint64_t nBlocks = (((uint64_t)ix.T - 1) >> shift) + 1;
-	const uint64_t W = (((nBlocks + 31) / 32) + 7) & ~uint64_t(7);
-	// a gram gets a bitmap when the bitmap is at most twice as large as its posting list — or always, on indexes so small
-	// that bitmaps for every gram stay within that budget overall
-	uint32_t minLen = (uint32_t)std::max<uint64_t>(1, W / 2);
-	if ((uint64_t)ix.G * W <= 2ull * ix.P + (1u << 18)) minLen = 1;
+	const uint64_t nGroups = (nBlocks + SIEVE_GROUP_BLOCKS - 1) / SIEVE_GROUP_BLOCKS;
+	// a gram gets a bitmap when the bitmap (16 bytes per group) is at most twice as large as its posting list — or always,
+	// on indexes so small that bitmaps for every gram stay within that budget overall
+	uint32_t minLen = (uint32_t)std::max<uint64_t>(1, 2 * nGroups);
+	if ((uint64_t)ix.G * nGroups * 4 <= 2ull * ix.P + (1u << 18)) minLen = 1;
 
 	DevBuf<uint8_t> flag(ix.G, s);
 	DevBuf<uint32_t> pos(ix.G, s), dN(1, s);
@@ -116,13 +115,11 @@ void build_sieve(DeviceIndex& ix, cudaStream_t s)
 	ix.sieveSlot.alloc(ix.G, s);
 	k_sieve_slots<<<grid_for(ix.G), TPB, 0, s>>>(flag.get(), pos.get(), ix.G, ix.sieveSlot.get(), gramOfSlot.get());
 	SSB_LAUNCH_CHECK();
-	ix.sieveBits.alloc((size_t)nSlots * W, s);
-	ix.sieveBits.zero(s);
-	ix.sieveCum.alloc((size_t)nSlots * (W / 8 + 1), s);
-	k_sieve_fill<<<nSlots, TPB, 0, s>>>(gramOfSlot.get(), ix.gramOff.get(), ix.postings.get(), shift, (uint32_t)W, ix.sieveBits.get(),
-	                                    ix.sieveCum.get());
+	ix.sieveGroups.alloc((size_t)nSlots * nGroups * 4, s);
+	ix.sieveGroups.zero(s);
+	k_sieve_fill<<<nSlots, TPB, 0, s>>>(gramOfSlot.get(), ix.gramOff.get(), ix.postings.get(), shift, (uint32_t)nGroups, ix.sieveGroups.get());
 	SSB_LAUNCH_CHECK();
-	ix.sieveShift = shift; ix.sieveWords = (uint32_t)W; ix.sieveSlots = nSlots;      // (scratch buffers are freed in stream order)
+	ix.sieveShift = shift; ix.sieveNGroups = (uint32_t)nGroups; ix.sieveSlots = nSlots;      // (scratch buffers are freed in stream order)
 }
 
 }   // namespace ssb

@@ -32,14 +32,14 @@ namespace {
 constexpr int SV_THREADS = 128;
 constexpr int SV_CCAP = 2048;                           // candidate blocks per pass
 constexpr int SV_PU = 4;                                // lists of one block resolved at a time (independent load chains)
-constexpr int SV_DISTINCT = 8;                          // distinct terms tracked per block
+constexpr int SV_SLOWCAP = 256;                         // blocks per pass that need the general resolution
 
 struct SieveShared {
-	const uint32_t* sievePtr[SV_MAXL];                  // bitmaps as the sieve counts them: list j repeated mult[j] times
-	const uint32_t* bitsPtr[SV_MAXL];                   // bitmap of list j
-	const uint32_t* cumPtr[SV_MAXL];                    // its group directory
+	const uint4* sievePtr[SV_MAXL];                     // group arrays as the sieve counts them: list j repeated mult[j] times
+	const uint4* grpPtr[SV_MAXL];                       // group array of list j: { first posting, 3 x 32 block bits } per 96 blocks
 	uint32_t listEnd[SV_MAXL], mult[SV_MAXL];
 	uint32_t cand[SV_CCAP];                             // numbers of the blocks that passed the sieve
+	uint32_t slowQ[SV_SLOWCAP];                         // of those, the ones left to resolve_slow
 	unsigned long long* buf;                            // candidate keys: bufCap entries behind this struct in dynamic smem
 	uint32_t bufCap;
 	uint32_t defCount, defCap;
@@ -57,8 +57,8 @@ struct SieveShared {
 	unsigned long long tau;
 	uint32_t promotedKey;
 	uint32_t bufCount, overflow, query, selPrefixLo, selK;
-	uint32_t nCand, nProbe;
-	uint32_t passW0, passW1, cRej, done;
+	uint32_t nCand, nProbe, nSlow;
+	uint32_t passG0, passG1, cRej, done;
 	uint32_t qlen, nGrams, cmin, cprom, nLists, sumMult;
 	uint32_t shortActive, scanLong, scanLongOnly;       // read by the shared scoring helpers; always 0 here
 	float threshold;
@@ -67,32 +67,29 @@ struct SieveShared {
 	IndexView ix;
 };
 
-__device__ __forceinline__ uint2 ldg_u2(const uint32_t* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
-
-// ---- SIEVE: words [w0, w1) (both even) of every list -> queue of blocks hit by >= CREQ lists. A list whose gram occurs m
-// times in the query appears m times in sievePtr (hpp:289-298 counts once per window), so the counter needs no multiplicities.
+// ---- SIEVE: groups [g0, g1) of every list -> queue of blocks hit by >= CREQ lists. A list whose gram occurs m times in the
+// query appears m times in sievePtr (hpp:289-298 counts once per window), so the counter needs no multiplicities.
 template <int CREQ>
-__device__ __forceinline__ void sieve_words(SieveShared& sh, const uint32_t w0, const uint32_t w1, const uint32_t nS)
+__device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, const uint32_t g1, const uint32_t nS)
 {
 	const int tid = threadIdx.x, lane = tid & 31;
-	for (uint32_t base = w0; base < w1; base += 2 * SV_THREADS) {
-		const uint32_t w = base + 2 * tid;
-		const bool act = w < w1;
-		uint32_t ga[CREQ], gb[CREQ];
+	for (uint32_t base = g0; base < g1; base += SV_THREADS) {
+		const uint32_t g = base + tid;
+		uint32_t ga[CREQ], gb[CREQ], gc[CREQ];
 #pragma unroll
-		for (int c = 0; c < CREQ; ++c) { ga[c] = 0; gb[c] = 0; }
-		if (act) {
+		for (int c = 0; c < CREQ; ++c) { ga[c] = 0; gb[c] = 0; gc[c] = 0; }
+		if (g < g1) {
 #pragma unroll 4
 			for (uint32_t j = 0; j < nS; ++j) {
-				const uint2 x = ldg_u2(sh.sievePtr[j] + w);
+				const uint4 x = __ldg(sh.sievePtr[j] + g);          // { first posting, 3 x 32 block bits }
 #pragma unroll
-				for (int c = CREQ - 1; c >= 1; --c) { ga[c] |= ga[c - 1] & x.x; gb[c] |= gb[c - 1] & x.y; }
-				ga[0] |= x.x; gb[0] |= x.y;
+				for (int c = CREQ - 1; c >= 1; --c) { ga[c] |= ga[c - 1] & x.y; gb[c] |= gb[c - 1] & x.z; gc[c] |= gc[c - 1] & x.w; }
+				ga[0] |= x.y; gb[0] |= x.z; gc[0] |= x.w;
 			}
 		}
-		uint32_t ma = ga[CREQ - 1], mb = gb[CREQ - 1];
-		if (!__any_sync(0xffffffffu, (ma | mb) != 0)) continue;
-		const uint32_t n = __popc(ma) + __popc(mb);
+		uint32_t ma = ga[CREQ - 1], mb = gb[CREQ - 1], mc = gc[CREQ - 1];
+		if (!__any_sync(0xffffffffu, (ma | mb | mc) != 0)) continue;
+		const uint32_t n = __popc(ma) + __popc(mb) + __popc(mc);
 		uint32_t inc = n;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -102,20 +99,25 @@ __device__ __forceinline__ void sieve_words(SieveShared& sh, const uint32_t w0, 
 		cBase = __shfl_sync(0xffffffffu, cBase, 31);
 		if (cBase + tot > SV_CCAP) continue;                    // pass too long: counted, redone shorter
 		uint32_t ci = cBase + inc - n;
-		while (ma) { sh.cand[ci++] = (w << 5) | (__ffs(ma) - 1); ma &= ma - 1; }
-		while (mb) { sh.cand[ci++] = ((w + 1) << 5) | (__ffs(mb) - 1); mb &= mb - 1; }
+		const uint32_t b0 = g * SIEVE_GROUP_BLOCKS;
+#pragma unroll 1
+		while (ma) { sh.cand[ci++] = b0 + (__ffs(ma) - 1); ma &= ma - 1; }
+#pragma unroll 1
+		while (mb) { sh.cand[ci++] = b0 + 32 + (__ffs(mb) - 1); mb &= mb - 1; }
+#pragma unroll 1
+		while (mc) { sh.cand[ci++] = b0 + 64 + (__ffs(mc) - 1); mc &= mc - 1; }
 	}
 }
 
-__device__ __forceinline__ void sieve_dispatch(SieveShared& sh, uint32_t creq, uint32_t w0, uint32_t w1, uint32_t nS)
+__device__ __forceinline__ void sieve_dispatch(SieveShared& sh, uint32_t creq, uint32_t g0, uint32_t g1, uint32_t nS)
 {
 	// thresholds without an instantiation of their own use the next lower one: a superset of the blocks, RESOLVE counts exactly
-	if (creq <= 1) sieve_words<1>(sh, w0, w1, nS);
-	else if (creq == 2) sieve_words<2>(sh, w0, w1, nS);
-	else if (creq == 3) sieve_words<3>(sh, w0, w1, nS);
-	else if (creq < 6) sieve_words<4>(sh, w0, w1, nS);
-	else if (creq < 8) sieve_words<6>(sh, w0, w1, nS);
-	else sieve_words<8>(sh, w0, w1, nS);
+	if (creq <= 1) sieve_groups<1>(sh, g0, g1, nS);
+	else if (creq == 2) sieve_groups<2>(sh, g0, g1, nS);
+	else if (creq == 3) sieve_groups<3>(sh, g0, g1, nS);
+	else if (creq < 6) sieve_groups<4>(sh, g0, g1, nS);
+	else if (creq < 8) sieve_groups<6>(sh, g0, g1, nS);
+	else sieve_groups<8>(sh, g0, g1, nS);
 }
 
 // a term with exact match count c > cRej (same tail as merge_pass); emits are rare -> one copy of the code
@@ -133,38 +135,41 @@ __device__ __noinline__ void sieve_emit(SieveShared& sh, uint32_t term, uint32_t
 	}
 }
 
-// position of the first posting of list j in block (grp * 8 + wi) * 32 + bit, given that the list's bitmap has the bit set:
-// directory entry of the 256-block group + number of occupied blocks below (exact unless one of those holds several postings)
-__device__ __forceinline__ uint32_t sieve_locate(const SieveShared& sh, uint32_t j, uint32_t grp, uint32_t wi, uint32_t bit)
+// group x of a list, block = word k / bit of the group: is the block's bit set, and where the block's first posting is —
+// the group's first posting + the occupied blocks below (exact unless one of those holds several postings)
+__device__ __forceinline__ bool sieve_locate(const uint4 x, uint32_t k, uint32_t bit, uint32_t& idx)
 {
-	const uint4* gp = reinterpret_cast<const uint4*>(sh.bitsPtr[j] + (grp << 3));
-	uint32_t idx = __ldg(sh.cumPtr[j] + grp);
-	const uint4 a = __ldg(gp), b = __ldg(gp + 1);
-	const uint32_t ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-	for (int t = 0; t < 8; ++t) {
-		const uint32_t m = (uint32_t)t < wi ? 0xFFFFFFFFu : ((uint32_t)t == wi ? ((1u << bit) - 1u) : 0u);
-		idx += __popc(ws[t] & m);
-	}
-	return idx;
+	const uint32_t wk = k == 0 ? x.y : (k == 1 ? x.z : x.w);
+	idx = x.x + (k > 0 ? __popc(x.y) : 0) + (k > 1 ? __popc(x.z) : 0) + __popc(wk & ((1u << bit) - 1u));
+	return (wk >> bit) & 1u;
 }
 
-// general resolution of one block (more than SV_PU lists hit it, or a list has several postings in it): one list at a
-// time into local arrays, counts by comparing all pairs. Rare.
-__device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_t lm, uint32_t cRej, uint32_t onlyCount, unsigned long long tau)
+// general resolution of one block (more than SV_PU lists hit it, or a list has several postings in or just below it):
+// local arrays, counts by comparing all pairs. Rare, and run for a compacted list of such blocks (see resolve_stage).
+__device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_t onlyCount, unsigned long long tau)
 {
 	constexpr int CAP = 48;
 	const int shift = sh.ix.sieveShift;
 	const uint32_t* __restrict__ postings = sh.ix.postings;
-	const uint32_t w = blk >> 5, bit = blk & 31u, grp = w >> 3, wi = w & 7u;
+	const uint32_t v = blk >> 5, g = v / 3u, k = v - 3u * g, bit = blk & 31u;
+	const uint32_t nL = sh.nLists;
+	uint32_t cRej = sh.cRej;
+	if (sh.classMode) {
+		const unsigned long long lo = (unsigned long long)blk << shift;
+		while (cRej < sh.nGrams && ((((unsigned long long)sh.hiKey[cRej + 1]) << 32) | lo) >= tau) ++cRej;
+	}
+	// the lists that hit the block and where (independent loads), then their postings inside the block
+	uint32_t lj[SV_MAXL], lp[SV_MAXL], ns = 0;
+#pragma unroll 4
+	for (uint32_t j = 0; j < nL; ++j) {
+		uint32_t p;
+		if (sieve_locate(__ldg(sh.grpPtr[j] + g), k, bit, p)) { lj[ns] = j; lp[ns] = p; ++ns; }
+	}
 	uint32_t ids[CAP], mus[CAP], m = 0;
-	while (lm) {
-		const uint32_t j = (uint32_t)__ffs(lm) - 1u;
-		lm &= lm - 1;
-		const uint32_t end = sh.listEnd[j], mu = sh.mult[j];
-		uint32_t p = sieve_locate(sh, j, grp, wi, bit);
+	for (uint32_t s = 0; s < ns; ++s) {
+		const uint32_t end = sh.listEnd[lj[s]], mu = sh.mult[lj[s]];
 		bool any = false;
-		for (; p < end; ++p) {
+		for (uint32_t p = lp[s]; p < end; ++p) {
 			const uint32_t id = __ldg(postings + p);
 			const uint32_t b = id >> shift;
 			if (b < blk) continue;                           // extra postings of lower blocks
@@ -195,62 +200,69 @@ __device__ __forceinline__ void resolve_stage(SieveShared& sh, const uint32_t nC
 	uint32_t probes = 0;
 	for (uint32_t i = threadIdx.x; i < nCand; i += SV_THREADS) {
 		const uint32_t blk = sh.cand[i];
-		const uint32_t w = blk >> 5, bit = blk & 31u, grp = w >> 3, wi = w & 7u;
-		// which lists hit the block (their words have just been streamed by the sieve: L1 / L2 hits)
-		uint32_t lm = 0;
+		const uint32_t v = blk >> 5, g = v / 3u, k = v - 3u * g, bit = blk & 31u;
+		// the block's group of every list (just streamed by the sieve: L1 / L2 hits): which lists hit the block, and where.
+		// Branch-free: the first SV_PU hits go to register slots, their lists to one nibble each of jp.
+		uint32_t idx[SV_PU], ns = 0, jp = 0;
+#pragma unroll
+		for (int u = 0; u < SV_PU; ++u) idx[u] = 0;
 #pragma unroll 4
-		for (uint32_t j = 0; j < nL; ++j) lm |= ((__ldg(sh.bitsPtr[j] + w) >> bit) & 1u) << j;
-		probes += __popc(lm);
+		for (uint32_t j = 0; j < nL; ++j) {
+			uint32_t p;
+			const bool hit = sieve_locate(__ldg(sh.grpPtr[j] + g), k, bit, p);
+#pragma unroll
+			for (int u = 0; u < SV_PU; ++u) idx[u] = (hit && ns == (uint32_t)u) ? p : idx[u];
+			jp |= (hit && ns < SV_PU) ? j << (4u * ns) : 0u;
+			ns += hit ? 1u : 0u;
+		}
+		probes += ns;
+		bool slow = ns > SV_PU;
+		uint32_t h[SV_PU], mu[SV_PU];
+		// Three postings per list decide the two common cases: the first one is the block's only posting of the list, or one
+		// extra posting of a lower block precedes it.
+#pragma unroll
+		for (int u = 0; u < SV_PU; ++u) {
+			const uint32_t j = (jp >> (4 * u)) & 15u;
+			const uint32_t end = (uint32_t)u < ns ? sh.listEnd[j] : 0u;
+			mu[u] = sh.mult[j];
+			const uint32_t id0 = idx[u] < end ? __ldg(postings + idx[u]) : INF;
+			const uint32_t id1 = idx[u] + 1 < end ? __ldg(postings + idx[u] + 1) : INF;
+			const uint32_t id2 = idx[u] + 2 < end ? __ldg(postings + idx[u] + 2) : INF;
+			const uint32_t b0 = id0 >> shift, b1 = id1 >> shift, b2 = id2 >> shift;
+			h[u] = INF;
+			if ((uint32_t)u < ns) {
+				if (b0 == blk && (id1 == INF || b1 != blk)) h[u] = id0;
+				else if (id0 != INF && b0 < blk && id1 != INF && b1 == blk && (id2 == INF || b2 != blk)) h[u] = id1;
+				else slow = true;
+			}
+		}
+		if (slow) {
+			// compacted and resolved after the loop, with every lane busy (inline, one such block would stall the whole warp)
+			const uint32_t si = atomicAdd(&sh.nSlow, 1u);
+			if (si < SV_SLOWCAP) sh.slowQ[si] = blk; else sh.overflow = 1;
+			continue;
+		}
 		// integer pre-filter refined by the block's first id (identity mode: kid == term id >= first id of the block)
 		uint32_t cRej = sh.cRej;
 		if (identMode) {
 			const unsigned long long lo = (unsigned long long)blk << shift;
 			while (cRej < nG && ((((unsigned long long)sh.hiKey[cRej + 1]) << 32) | lo) >= tau) ++cRej;
 		}
-		bool slow = __popc(lm) > SV_PU;
-		if (!slow) {
-			// up to SV_PU lists: independent load chains, everything stays in registers
-			uint32_t h[SV_PU], mu[SV_PU], idx[SV_PU], end[SV_PU], id0[SV_PU], id1[SV_PU];
-			bool on[SV_PU];
-			uint32_t rest = lm;
 #pragma unroll
-			for (int u = 0; u < SV_PU; ++u) {
-				on[u] = rest != 0;
-				const uint32_t j = on[u] ? (uint32_t)__ffs(rest) - 1u : 0u;
-				rest &= rest - 1;
-				idx[u] = on[u] ? sieve_locate(sh, j, grp, wi, bit) : 0u;
-				end[u] = on[u] ? sh.listEnd[j] : 0u;
-				mu[u] = sh.mult[j];
-			}
+		for (int u = 0; u < SV_PU; ++u) {
+			if ((uint32_t)u >= ns) continue;
+			uint32_t c = 0;
+			bool first = true;
 #pragma unroll
-			for (int u = 0; u < SV_PU; ++u) {
-				id0[u] = idx[u] < end[u] ? __ldg(postings + idx[u]) : INF;
-				id1[u] = idx[u] + 1 < end[u] ? __ldg(postings + idx[u] + 1) : INF;
-			}
-#pragma unroll
-			for (int u = 0; u < SV_PU; ++u) {
-				h[u] = INF;
-				if (!on[u]) continue;
-				// the common case: the first posting read is the block's only posting of the list; anything else -> general path
-				if ((id0[u] >> shift) != blk || (id1[u] != INF && (id1[u] >> shift) == blk)) slow = true;
-				h[u] = id0[u];
-			}
-			if (!slow) {
-#pragma unroll
-				for (int u = 0; u < SV_PU; ++u) {
-					if (!on[u]) continue;
-					uint32_t c = 0;
-					bool first = true;
-#pragma unroll
-					for (int v = 0; v < SV_PU; ++v)
-						if (on[v] && h[v] == h[u]) { c += mu[v]; if (v < u) first = false; }
-					if (first && c > cRej && (!onlyCount || c == onlyCount)) sieve_emit(sh, h[u], c, tau);
-				}
-			}
+			for (int w = 0; w < SV_PU; ++w)
+				if ((uint32_t)w < ns && h[w] == h[u]) { c += mu[w]; if (w < u) first = false; }
+			if (first && c > cRej && (!onlyCount || c == onlyCount)) sieve_emit(sh, h[u], c, tau);
 		}
-		if (slow) resolve_slow(sh, blk, lm, cRej, onlyCount, tau);
 	}
 	if (probes) atomicAdd(&sh.nProbe, probes);
+	__syncthreads();
+	const uint32_t nSlow = min(sh.nSlow, (uint32_t)SV_SLOWCAP);
+	for (uint32_t i = threadIdx.x; i < nSlow; i += SV_THREADS) resolve_slow(sh, sh.slowQ[i], onlyCount, tau);
 }
 
 // expected candidate blocks per bitmap word when a block needs >= c of K lists, every list setting a block with probability p
@@ -279,10 +291,9 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t nFast = counters[0];
 	const uint32_t k = limit;
-	const uint32_t W = ix.sieveWords, nGroups1 = (W >> 3) + 1;
+	const uint32_t NG = ix.sieveNGroups;
 	const int shift = ix.sieveShift;
 	const uint32_t nBlocks = (uint32_t)((((unsigned long long)ix.T - 1) >> shift) + 1);
-	const uint32_t Wused = (((nBlocks + 31) >> 5) + 1) & ~1u;          // even: the sieve reads word pairs (W % 8 == 0 covers it)
 	if (tid == 0) {
 		sh.ix = ix;
 		sh.buf = reinterpret_cast<unsigned long long*>(sv_smem + ((sizeof(SieveShared) + 15) & ~size_t(15)));
@@ -310,15 +321,13 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 		const float dens = fminf(1.0f, (float)d.total / ((float)nLists * (float)nBlocks));
 		if (tid < SV_MAXL) {
 			if ((uint32_t)tid < nLists) {
-				const uint32_t slot = d.listSlot[tid];
-				sh.bitsPtr[tid] = ix.sieveBits + (size_t)slot * W;
-				sh.cumPtr[tid] = ix.sieveCum + (size_t)slot * nGroups1;
+				sh.grpPtr[tid] = ix.sieveGroups + (size_t)d.listSlot[tid] * NG;
 				sh.listEnd[tid] = d.listOff[tid] + d.listLen[tid];
 				sh.mult[tid] = d.listMult[tid];
-			} else { sh.bitsPtr[tid] = ix.sieveBits; sh.cumPtr[tid] = ix.sieveCum; sh.listEnd[tid] = 0; sh.mult[tid] = 0; }
+			} else { sh.grpPtr[tid] = ix.sieveGroups; sh.listEnd[tid] = 0; sh.mult[tid] = 0; }
 		} else if (tid >= 32 && tid < 32 + 9) {
 			const uint32_t c = tid - 32;
-			sh.rateTab[c] = fmaxf(sieve_rate(nLists, max(c, 1u), dens), 1e-4f);
+			sh.rateTab[c] = fmaxf(3.0f * sieve_rate(nLists, max(c, 1u), dens), 1e-4f);      // per 96-block group
 		}
 		if (tid < MAX_QGRAMS) sh.qcode[tid] = (uint32_t)tid < nGrams ? d.qcode[tid] : ~0ull;
 		const bool classMode = ix.identity && ix.uniformW;
@@ -349,7 +358,7 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 			uint32_t sum = 0;
 			for (uint32_t i = 0; i < nLists; ++i)
 				for (uint32_t r = 0; r < d.listMult[i]; ++r) {
-					if (sum < SV_MAXL) sh.sievePtr[sum] = ix.sieveBits + (size_t)d.listSlot[i] * W;
+					if (sum < SV_MAXL) sh.sievePtr[sum] = ix.sieveGroups + (size_t)d.listSlot[i] * NG;
 					++sum;
 				}
 			sh.sumMult = sum;
@@ -378,13 +387,13 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 				}
 			} else if (tid == 0) sh.tau = ((unsigned long long)sh.exactKey[1]) << 32;      // "< tau": two or more matches
 			const uint32_t onlyCount = (twoPhase && phase == 1) ? 1u : 0u;
-			uint32_t wLo = 0, lastW1 = 0;
+			uint32_t gLo = 0, lastG1 = 0;
 			uint32_t lastCreq = 0, lastLen = 0, lastCands = 0, forceLen = 0;
-			while (wLo < Wused) {
+			while (gLo < NG) {
 				__syncthreads();                      // the previous pass is complete (its counters and plan have been read)
 				// ---- warp 0: tau from the counts of the pass just finished, the count a term needs from here on, the next pass
 				if (warp == 0) {
-					if (classMode && lastW1) {
+					if (classMode && lastG1) {
 						// k candidates with >= c matches are known, all of them below the end of the last pass: (class of c, end
 						// of that pass) bounds the k-th best. One warp scan; the select only runs to make room in the buffer.
 						const uint32_t c = lane + 1;
@@ -394,7 +403,7 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 						const unsigned m = __ballot_sync(0xffffffffu, h >= k);
 						if (lane == 0 && m) {
 							const uint32_t cb = 32u - (uint32_t)__clz(m);
-							const unsigned long long hiId = min(((unsigned long long)lastW1 << 5) << shift, 0xFFFFFFFFull);
+							const unsigned long long hiId = min(((unsigned long long)lastG1 * SIEVE_GROUP_BLOCKS) << shift, 0xFFFFFFFFull);
 							const unsigned long long t2 = (((unsigned long long)sh.exactKey[cb]) << 32) | hiId;
 							if (t2 < sh.tau) sh.tau = t2;
 						}
@@ -404,7 +413,7 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 					uint32_t rej = sh.cmin ? sh.cmin - 1 : 0;
 					const unsigned long long tau = sh.tau;
 					unsigned long long lowKid = 0;
-					if (classMode) lowKid = min(((unsigned long long)wLo << 5) << shift, 0xFFFFFFFFull);
+					if (classMode) lowKid = min(((unsigned long long)gLo * SIEVE_GROUP_BLOCKS) << shift, 0xFFFFFFFFull);
 					const uint32_t c = rej + 1 + lane;
 					const bool out = c <= nGrams && ((((unsigned long long)sh.hiKey[min(c, (uint32_t)MAX_QGRAMS)]) << 32) | lowKid) >= tau;
 					const unsigned mOut = __ballot_sync(0xffffffffu, out);
@@ -422,17 +431,16 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 							if (creq <= 1) want = min(want, classMode ? bufCap - level : min(sh.defCap, bufCap - level));
 							const float rate = (creq == lastCreq && lastLen) ? fmaxf(1.25f * (float)lastCands / (float)lastLen, 1e-4f) : sh.rateTab[min(creq, 8u)];
 							const float l = 0.7f * (float)want / rate;
-							len = l >= (float)Wused ? Wused : max(2u, (uint32_t)l);
-							if (len > 8 * SV_THREADS) len &= ~(uint32_t)(2 * SV_THREADS - 1);
+							len = l >= (float)NG ? NG : max(1u, (uint32_t)l);
+							if (len > 8 * SV_THREADS) len &= ~(uint32_t)(SV_THREADS - 1);
 						}
-						len = (len + 1) & ~1u;
-						sh.passW0 = wLo; sh.passW1 = min(Wused, wLo + len);
-						sh.nCand = 0; sh.defCount = 0;
+						sh.passG0 = gLo; sh.passG1 = min(NG, gLo + len);
+						sh.nCand = 0; sh.nSlow = 0; sh.defCount = 0;
 					}
 				}
 				__syncthreads();
 				if (sh.done) break;
-				const uint32_t w0 = sh.passW0, w1 = sh.passW1, creq = sh.cRej + 1;
+				const uint32_t w0 = sh.passG0, w1 = sh.passG1, creq = sh.cRej + 1;
 				if (tid == 0) atomicAdd(&counters[24], 1u);
 				// ---- sieve
 				sieve_dispatch(sh, creq, w0, w1, nSieve);
@@ -465,15 +473,15 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 					}
 				}
 				if (redo) {
-					if (w1 - w0 <= 2) { failed = true; break; }
-					forceLen = max(2u, shorter);
+					if (w1 - w0 <= 1) { failed = true; break; }
+					forceLen = max(1u, shorter);
 					if (tid == 0) atomicAdd(&counters[27], 1u);
 					continue;
 				}
 				forceLen = 0;
 				if (tid == 0) { atomicAdd(&counters[26], nCand); }
 				lastCreq = creq; lastLen = w1 - w0; lastCands = nCand + 1;
-				wLo = w1; lastW1 = w1;
+				gLo = w1; lastG1 = w1;
 				level = sh.bufCount;
 				// ---- make room / establish tau where the counts cannot (weights: values are not classes)
 				if (classMode) {
