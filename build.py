@@ -17,7 +17,7 @@ LIB = os.path.join(ROOT, "stringsearchlib_b200", "lib")
 OBJ = os.path.join(ROOT, "build", "obj")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CUFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"] + ARCH
+CUFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"] + ARCH + os.environ.get("SSB_NVCC_FLAGS", "").split()
 CU = ["primitives.cu", "build.cu", "sieve.cu", "search.cu", "merge.cu", "engine.cu"]
 
 

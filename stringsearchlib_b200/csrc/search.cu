@@ -540,8 +540,8 @@ void ensure_workspace(SearchWorkspace& ws, uint32_t nq, size_t charBytes, uint32
 	if (!ws.ev0) {
 		SSB_CUDA(cudaEventCreate(&ws.ev0)); SSB_CUDA(cudaEventCreate(&ws.ev1));
 		SSB_CUDA(cudaEventCreate(&ws.ev2)); SSB_CUDA(cudaEventCreate(&ws.ev3));
-		ws.counters.alloc(32, s);
-		ws.hostCounters.reserve(32);
+		ws.counters.alloc(64, s);
+		ws.hostCounters.reserve(64);
 	}
 	if (nq > ws.capQ || stride > ws.stride) {
 		uint32_t cq = std::max(nq, ws.capQ), st = std::max(stride, ws.stride);
@@ -708,7 +708,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		SSB_CUDA(cudaStreamSynchronize(s));
 	} else {
 		if (csr && !direct) enqueue_finalize();
-		SSB_CUDA(cudaMemcpyAsync(hc, ws.counters.get(), 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		SSB_CUDA(cudaMemcpyAsync(hc, ws.counters.get(), 64 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 		SSB_CUDA(cudaEventRecord(ws.ev3, s));
 		SSB_CUDA(cudaEventSynchronize(ws.ev3));
 	}
@@ -759,6 +759,11 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		if (dbg && hc[6])
 			fprintf(stderr, "[ssb] k_sieve_search per query: %.1f passes (%.2f redone), %.0f candidate blocks, %.0f probes; gave up on %u\n",
 			        hc[24] / (double)hc[6], hc[27] / (double)hc[6], hc[26] / (double)hc[6], hc[25] / (double)hc[6], hc[28]);
+		if (dbg && hc[6] && hc[34])
+			fprintf(stderr, "[ssb] k_sieve_search kilocycles per query: set-up %.1f, plan %.1f, sieve+resolve %.1f, slow+deferred %.1f, select %.1f, final %.1f\n",
+			        hc[32] * 0.064 / hc[6], hc[33] * 0.064 / hc[6], hc[34] * 0.064 / hc[6], hc[35] * 0.064 / hc[6], hc[36] * 0.064 / hc[6], hc[37] * 0.064 / hc[6]),
+			fprintf(stderr, "[ssb]   of sieve+resolve, warp 0: loads + counters %.1f, queue pushes %.1f, resolve rounds %.1f\n", hc[40] * 0.064 / hc[6],
+			        hc[41] * 0.064 / hc[6], hc[42] * 0.064 / hc[6]);
 		st->postingsTouched = postings;
 		st->msDevice = st->msFastKernel = 0;
 		if (!tiny) {

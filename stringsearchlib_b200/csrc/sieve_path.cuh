@@ -29,8 +29,23 @@
 
 namespace {
 
+// -DSV_TIMING=1: thread 0 of every CTA accumulates the cycles (>> 6) it spends per phase of a query into counters[32..39]
+// (0 set-up, 1 plan, 2 sieve + resolve, 3 slow blocks + deferred, 4 select in the loop, 5 final select + sort + output)
+#ifndef SV_TIMING
+#define SV_TIMING 0
+#endif
+#if SV_TIMING
+#define SV_TICK(slot) do { if (tid == 0) { const long long t_ = clock64(); atomicAdd(&counters[32 + (slot)], (uint32_t)((t_ - tick) >> 6)); tick = t_; } } while (0)
+#else
+#define SV_TICK(slot) do { } while (0)
+#endif
+
+#ifndef SV_MIN_CTAS
+#define SV_MIN_CTAS 8
+#endif
 constexpr int SV_THREADS = 128;
-constexpr int SV_CCAP = 2048;                           // candidate blocks per pass
+constexpr int SV_CCAP = 1024;                           // candidate blocks a pass aims at (its length is chosen accordingly)
+constexpr int SV_WQCAP = 160;                           // per-warp queue of blocks that passed the sieve: < 32 left over + <= 128 pushed
 constexpr int SV_PU = 4;                                // lists of one block resolved at a time (independent load chains)
 constexpr int SV_SLOWCAP = 256;                         // blocks per pass that need the general resolution
 
@@ -38,7 +53,7 @@ struct SieveShared {
 	const uint4* sievePtr[SV_MAXL];                     // group arrays as the sieve counts them: list j repeated mult[j] times
 	const uint4* grpPtr[SV_MAXL];                       // group array of list j: { first posting, 3 x 32 block bits } per 96 blocks
 	uint32_t listEnd[SV_MAXL], mult[SV_MAXL];
-	uint32_t cand[SV_CCAP];                             // numbers of the blocks that passed the sieve
+	uint32_t wq[SV_THREADS / 32][SV_WQCAP];             // numbers of the blocks that passed the sieve, per warp
 	uint32_t slowQ[SV_SLOWCAP];                         // of those, the ones left to resolve_slow
 	unsigned long long* buf;                            // candidate keys: bufCap entries behind this struct in dynamic smem
 	uint32_t bufCap;
@@ -58,6 +73,7 @@ struct SieveShared {
 	uint32_t promotedKey;
 	uint32_t bufCount, overflow, query, selPrefixLo, selK;
 	uint32_t nCand, nProbe, nSlow;
+	uint32_t tim[4];                                    // SV_TIMING: warp 0's cycles >> 6 in the sieve loads, the queue pushes, the resolve rounds
 	uint32_t passG0, passG1, cRej, done;
 	uint32_t qlen, nGrams, cmin, cprom, nLists, sumMult;
 	uint32_t shortActive, scanLong, scanLongOnly;       // read by the shared scoring helpers; always 0 here
@@ -66,59 +82,6 @@ struct SieveShared {
 	uint32_t classMode;
 	IndexView ix;
 };
-
-// ---- SIEVE: groups [g0, g1) of every list -> queue of blocks hit by >= CREQ lists. A list whose gram occurs m times in the
-// query appears m times in sievePtr (hpp:289-298 counts once per window), so the counter needs no multiplicities.
-template <int CREQ>
-__device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, const uint32_t g1, const uint32_t nS)
-{
-	const int tid = threadIdx.x, lane = tid & 31;
-	for (uint32_t base = g0; base < g1; base += SV_THREADS) {
-		const uint32_t g = base + tid;
-		uint32_t ga[CREQ], gb[CREQ], gc[CREQ];
-#pragma unroll
-		for (int c = 0; c < CREQ; ++c) { ga[c] = 0; gb[c] = 0; gc[c] = 0; }
-		if (g < g1) {
-#pragma unroll 4
-			for (uint32_t j = 0; j < nS; ++j) {
-				const uint4 x = __ldg(sh.sievePtr[j] + g);          // { first posting, 3 x 32 block bits }
-#pragma unroll
-				for (int c = CREQ - 1; c >= 1; --c) { ga[c] |= ga[c - 1] & x.y; gb[c] |= gb[c - 1] & x.z; gc[c] |= gc[c - 1] & x.w; }
-				ga[0] |= x.y; gb[0] |= x.z; gc[0] |= x.w;
-			}
-		}
-		uint32_t ma = ga[CREQ - 1], mb = gb[CREQ - 1], mc = gc[CREQ - 1];
-		if (!__any_sync(0xffffffffu, (ma | mb | mc) != 0)) continue;
-		const uint32_t n = __popc(ma) + __popc(mb) + __popc(mc);
-		uint32_t inc = n;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-		const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-		uint32_t cBase = 0;
-		if (lane == 31) cBase = atomicAdd(&sh.nCand, tot);
-		cBase = __shfl_sync(0xffffffffu, cBase, 31);
-		if (cBase + tot > SV_CCAP) continue;                    // pass too long: counted, redone shorter
-		uint32_t ci = cBase + inc - n;
-		const uint32_t b0 = g * SIEVE_GROUP_BLOCKS;
-#pragma unroll 1
-		while (ma) { sh.cand[ci++] = b0 + (__ffs(ma) - 1); ma &= ma - 1; }
-#pragma unroll 1
-		while (mb) { sh.cand[ci++] = b0 + 32 + (__ffs(mb) - 1); mb &= mb - 1; }
-#pragma unroll 1
-		while (mc) { sh.cand[ci++] = b0 + 64 + (__ffs(mc) - 1); mc &= mc - 1; }
-	}
-}
-
-__device__ __forceinline__ void sieve_dispatch(SieveShared& sh, uint32_t creq, uint32_t g0, uint32_t g1, uint32_t nS)
-{
-	// thresholds without an instantiation of their own use the next lower one: a superset of the blocks, RESOLVE counts exactly
-	if (creq <= 1) sieve_groups<1>(sh, g0, g1, nS);
-	else if (creq == 2) sieve_groups<2>(sh, g0, g1, nS);
-	else if (creq == 3) sieve_groups<3>(sh, g0, g1, nS);
-	else if (creq < 6) sieve_groups<4>(sh, g0, g1, nS);
-	else if (creq < 8) sieve_groups<6>(sh, g0, g1, nS);
-	else sieve_groups<8>(sh, g0, g1, nS);
-}
 
 // a term with exact match count c > cRej (same tail as merge_pass); emits are rare -> one copy of the code
 __device__ __noinline__ void sieve_emit(SieveShared& sh, uint32_t term, uint32_t c, unsigned long long tau)
@@ -145,7 +108,7 @@ __device__ __forceinline__ bool sieve_locate(const uint4 x, uint32_t k, uint32_t
 }
 
 // general resolution of one block (more than SV_PU lists hit it, or a list has several postings in or just below it):
-// local arrays, counts by comparing all pairs. Rare, and run for a compacted list of such blocks (see resolve_stage).
+// local arrays, counts by comparing all pairs. Rare, and run for a compacted list of such blocks after the pass.
 __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_t onlyCount, unsigned long long tau)
 {
 	constexpr int CAP = 48;
@@ -158,24 +121,32 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 		const unsigned long long lo = (unsigned long long)blk << shift;
 		while (cRej < sh.nGrams && ((((unsigned long long)sh.hiKey[cRej + 1]) << 32) | lo) >= tau) ++cRej;
 	}
-	// the lists that hit the block and where (independent loads), then their postings inside the block
-	uint32_t lj[SV_MAXL], lp[SV_MAXL], ns = 0;
+	// the lists that hit the block (word k of every list's group: independent loads), then per list the postings inside the
+	// block, four in flight at a time
+	uint32_t lm = 0;
 #pragma unroll 4
-	for (uint32_t j = 0; j < nL; ++j) {
-		uint32_t p;
-		if (sieve_locate(__ldg(sh.grpPtr[j] + g), k, bit, p)) { lj[ns] = j; lp[ns] = p; ++ns; }
-	}
+	for (uint32_t j = 0; j < nL; ++j) lm |= ((__ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + g) + 1 + k) >> bit) & 1u) << j;
 	uint32_t ids[CAP], mus[CAP], m = 0;
-	for (uint32_t s = 0; s < ns; ++s) {
-		const uint32_t end = sh.listEnd[lj[s]], mu = sh.mult[lj[s]];
-		bool any = false;
-		for (uint32_t p = lp[s]; p < end; ++p) {
-			const uint32_t id = __ldg(postings + p);
-			const uint32_t b = id >> shift;
-			if (b < blk) continue;                           // extra postings of lower blocks
-			if (b > blk) break;
-			if (m < CAP) { ids[m] = id; mus[m] = mu; ++m; } else sh.overflow = 2;
-			any = true;
+	while (lm) {
+		const uint32_t j = (uint32_t)__ffs(lm) - 1u;
+		lm &= lm - 1;
+		uint32_t p;
+		sieve_locate(__ldg(sh.grpPtr[j] + g), k, bit, p);
+		const uint32_t end = sh.listEnd[j], mu = sh.mult[j];
+		bool any = false, more = true;
+		while (more && p < end) {
+			uint32_t id[4];
+#pragma unroll
+			for (int t = 0; t < 4; ++t) id[t] = p + t < end ? __ldg(postings + p + t) : INF;
+#pragma unroll
+			for (int t = 0; t < 4; ++t) {
+				const uint32_t b = id[t] >> shift;
+				if (id[t] == INF || b > blk) { more = false; break; }
+				if (b < blk) continue;                       // extra postings of lower blocks
+				if (m < CAP) { ids[m] = id[t]; mus[m] = mu; ++m; } else sh.overflow = 2;
+				any = true;
+			}
+			p += 4;
 		}
 		if (!any) sh.overflow = 2;                           // bitmap and postings disagree: never trust, hand the query over
 	}
@@ -188,81 +159,187 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 	}
 }
 
-// ---- RESOLVE: one thread per queued block. onlyCount != 0: emit only terms with exactly that many matches (second
-// phase: the others are in the buffer already).
-__device__ __forceinline__ void resolve_stage(SieveShared& sh, const uint32_t nCand, const uint32_t nL, const uint32_t onlyCount)
+// ---- RESOLVE one block that passed the sieve (one thread per block, a full warp of blocks at a time). Returns the number
+// of lists that hit it. onlyCount != 0: emit only terms with exactly that many matches (second phase: the others are in the
+// buffer already).
+__device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t blk, const uint32_t onlyCount, const unsigned long long tau)
 {
-	const bool identMode = sh.classMode != 0;
-	const unsigned long long tau = sh.tau;
-	const uint32_t nG = sh.nGrams;
 	const int shift = sh.ix.sieveShift;
 	const uint32_t* __restrict__ postings = sh.ix.postings;
-	uint32_t probes = 0;
-	for (uint32_t i = threadIdx.x; i < nCand; i += SV_THREADS) {
-		const uint32_t blk = sh.cand[i];
-		const uint32_t v = blk >> 5, g = v / 3u, k = v - 3u * g, bit = blk & 31u;
-		// the block's group of every list (just streamed by the sieve: L1 / L2 hits): which lists hit the block, and where.
-		// Branch-free: the first SV_PU hits go to register slots, their lists to one nibble each of jp.
-		uint32_t idx[SV_PU], ns = 0, jp = 0;
+	const uint32_t nL = sh.nLists;
+	const uint32_t v = blk >> 5, g = v / 3u, k = v - 3u * g, bit = blk & 31u;
+	// Three waits per block, each for independent loads: (1) word k of every list's group (streamed by this warp moments ago:
+	// L1 / L2 hits) -> which lists hit the block; (2) the whole group of the first SV_PU of them -> where the block's first
+	// posting is: the group's first posting + the occupied blocks below (exact unless one of those holds several); (3) postings.
+	uint32_t lm = 0;
+	{
+		uint32_t wv[SV_MAXL];
 #pragma unroll
-		for (int u = 0; u < SV_PU; ++u) idx[u] = 0;
-#pragma unroll 4
-		for (uint32_t j = 0; j < nL; ++j) {
-			uint32_t p;
-			const bool hit = sieve_locate(__ldg(sh.grpPtr[j] + g), k, bit, p);
+		for (int j = 0; j < SV_MAXL; ++j)
+			wv[j] = (uint32_t)j < nL ? __ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + g) + 1 + k) : 0u;
 #pragma unroll
-			for (int u = 0; u < SV_PU; ++u) idx[u] = (hit && ns == (uint32_t)u) ? p : idx[u];
-			jp |= (hit && ns < SV_PU) ? j << (4u * ns) : 0u;
-			ns += hit ? 1u : 0u;
-		}
-		probes += ns;
-		bool slow = ns > SV_PU;
-		uint32_t h[SV_PU], mu[SV_PU];
-		// Three postings per list decide the two common cases: the first one is the block's only posting of the list, or one
-		// extra posting of a lower block precedes it.
+		for (int j = 0; j < SV_MAXL; ++j) lm |= ((wv[j] >> bit) & 1u) << j;
+	}
+	const uint32_t ns = __popc(lm);
+	const uint32_t low = (1u << bit) - 1u;
+	const uint32_t my = k == 0 ? low : 0xFFFFFFFFu, mz = k == 1 ? low : (k > 1 ? 0xFFFFFFFFu : 0u), mw = k == 2 ? low : 0u;
+	uint32_t idx[SV_PU], jp = 0;
+	{
+		uint4 x[SV_PU];
+		uint32_t rest = lm;
 #pragma unroll
 		for (int u = 0; u < SV_PU; ++u) {
-			const uint32_t j = (jp >> (4 * u)) & 15u;
-			const uint32_t end = (uint32_t)u < ns ? sh.listEnd[j] : 0u;
-			mu[u] = sh.mult[j];
-			const uint32_t id0 = idx[u] < end ? __ldg(postings + idx[u]) : INF;
-			const uint32_t id1 = idx[u] + 1 < end ? __ldg(postings + idx[u] + 1) : INF;
-			const uint32_t id2 = idx[u] + 2 < end ? __ldg(postings + idx[u] + 2) : INF;
-			const uint32_t b0 = id0 >> shift, b1 = id1 >> shift, b2 = id2 >> shift;
-			h[u] = INF;
-			if ((uint32_t)u < ns) {
-				if (b0 == blk && (id1 == INF || b1 != blk)) h[u] = id0;
-				else if (id0 != INF && b0 < blk && id1 != INF && b1 == blk && (id2 == INF || b2 != blk)) h[u] = id1;
-				else slow = true;
-			}
-		}
-		if (slow) {
-			// compacted and resolved after the loop, with every lane busy (inline, one such block would stall the whole warp)
-			const uint32_t si = atomicAdd(&sh.nSlow, 1u);
-			if (si < SV_SLOWCAP) sh.slowQ[si] = blk; else sh.overflow = 1;
-			continue;
-		}
-		// integer pre-filter refined by the block's first id (identity mode: kid == term id >= first id of the block)
-		uint32_t cRej = sh.cRej;
-		if (identMode) {
-			const unsigned long long lo = (unsigned long long)blk << shift;
-			while (cRej < nG && ((((unsigned long long)sh.hiKey[cRej + 1]) << 32) | lo) >= tau) ++cRej;
+			const uint32_t j = rest ? (uint32_t)__ffs(rest) - 1u : 0u;
+			x[u] = rest ? __ldg(sh.grpPtr[j] + g) : make_uint4(0, 0, 0, 0);
+			jp |= j << (4 * u);
+			rest &= rest - 1;
 		}
 #pragma unroll
-		for (int u = 0; u < SV_PU; ++u) {
-			if ((uint32_t)u >= ns) continue;
-			uint32_t c = 0;
-			bool first = true;
+		for (int u = 0; u < SV_PU; ++u) idx[u] = x[u].x + __popc(x[u].y & my) + __popc(x[u].z & mz) + __popc(x[u].w & mw);
+	}
+	bool slow = ns > SV_PU;
+	uint32_t h[SV_PU], mu[SV_PU];
+	// Three postings per list decide the two common cases: the first one is the block's only posting of the list, or one
+	// extra posting of a lower block precedes it.
 #pragma unroll
-			for (int w = 0; w < SV_PU; ++w)
-				if ((uint32_t)w < ns && h[w] == h[u]) { c += mu[w]; if (w < u) first = false; }
-			if (first && c > cRej && (!onlyCount || c == onlyCount)) sieve_emit(sh, h[u], c, tau);
+	for (int u = 0; u < SV_PU; ++u) {
+		const uint32_t j = (jp >> (4 * u)) & 15u;
+		const uint32_t end = (uint32_t)u < ns ? sh.listEnd[j] : 0u;
+		mu[u] = sh.mult[j];
+		const uint32_t id0 = idx[u] < end ? __ldg(postings + idx[u]) : INF;
+		const uint32_t id1 = idx[u] + 1 < end ? __ldg(postings + idx[u] + 1) : INF;
+		const uint32_t id2 = idx[u] + 2 < end ? __ldg(postings + idx[u] + 2) : INF;
+		const uint32_t b0 = id0 >> shift, b1 = id1 >> shift, b2 = id2 >> shift;
+		h[u] = INF;
+		if ((uint32_t)u < ns) {
+			if (b0 == blk && (id1 == INF || b1 != blk)) h[u] = id0;
+			else if (id0 != INF && b0 < blk && id1 != INF && b1 == blk && (id2 == INF || b2 != blk)) h[u] = id1;
+			else slow = true;
 		}
 	}
-	if (probes) atomicAdd(&sh.nProbe, probes);
-	__syncthreads();
-	const uint32_t nSlow = min(sh.nSlow, (uint32_t)SV_SLOWCAP);
-	for (uint32_t i = threadIdx.x; i < nSlow; i += SV_THREADS) resolve_slow(sh, sh.slowQ[i], onlyCount, tau);
+	if (slow) {
+		// compacted and resolved after the pass, with every lane busy (inline, one such block would stall the whole warp)
+		const uint32_t si = atomicAdd(&sh.nSlow, 1u);
+		if (si < SV_SLOWCAP) sh.slowQ[si] = blk; else sh.overflow = 1;
+		return ns;
+	}
+	// integer pre-filter refined by the block's first id (identity mode: kid == term id >= first id of the block)
+	uint32_t cRej = sh.cRej;
+	if (sh.classMode) {
+		const unsigned long long lo = (unsigned long long)blk << shift;
+		while (cRej < sh.nGrams && ((((unsigned long long)sh.hiKey[cRej + 1]) << 32) | lo) >= tau) ++cRej;
+	}
+#pragma unroll
+	for (int u = 0; u < SV_PU; ++u) {
+		if ((uint32_t)u >= ns) continue;
+		uint32_t c = 0;
+		bool first = true;
+#pragma unroll
+		for (int w = 0; w < SV_PU; ++w)
+			if ((uint32_t)w < ns && h[w] == h[u]) { c += mu[w]; if (w < u) first = false; }
+		if (first && c > cRej && (!onlyCount || c == onlyCount)) sieve_emit(sh, h[u], c, tau);
+	}
+	return ns;
+}
+
+// ---- SIEVE + RESOLVE over groups [g0, g1). A list whose gram occurs m times in the query appears m times in sievePtr
+// (hpp:289-298 counts once per window), so the threshold counter needs no multiplicities. Every warp streams 32 consecutive
+// groups per step, collects the blocks that pass in a queue of its own and resolves them 32 at a time — while the groups it
+// needs again are still in L1, without a CTA-wide barrier, and while the other warps keep streaming.
+template <int CREQ>
+__device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, const uint32_t g1, const uint32_t nS, const uint32_t onlyCount)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned long long tau = sh.tau;
+	uint32_t* wq = sh.wq[warp];
+	uint32_t qn = 0, nc = 0, np = 0;                             // queue fill (warp-uniform); statistics
+	// a warp streams 64 consecutive groups per step, two per lane (all 2 * nS loads of a lane are independent)
+	for (uint32_t base = g0 + warp * 64; base < g1; base += 2 * SV_THREADS) {
+		const uint32_t gA = base + lane, gB = gA + 32;
+#if SV_TIMING
+		long long tk = clock64();
+#define SV_TICKW(slot) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&sh.tim[slot], (uint32_t)((t_ - tk) >> 6)); tk = t_; } } while (0)
+#else
+#define SV_TICKW(slot) do { } while (0)
+#endif
+		uint32_t m[6];                                            // blocks that pass: 3 words of group A, 3 of group B
+		{
+			uint32_t ga[CREQ], gb[CREQ], gc[CREQ], ha[CREQ], hb[CREQ], hc[CREQ];
+#pragma unroll
+			for (int c = 0; c < CREQ; ++c) { ga[c] = 0; gb[c] = 0; gc[c] = 0; ha[c] = 0; hb[c] = 0; hc[c] = 0; }
+			const bool onA = gA < g1, onB = gB < g1;
+#pragma unroll 4
+			for (uint32_t j = 0; j < nS; ++j) {
+				const uint4* ptr = sh.sievePtr[j];
+				const uint4 x = onA ? __ldg(ptr + gA) : make_uint4(0, 0, 0, 0);      // { first posting, 3 x 32 block bits }
+				const uint4 y = onB ? __ldg(ptr + gB) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+				for (int c = CREQ - 1; c >= 1; --c) {
+					ga[c] |= ga[c - 1] & x.y; gb[c] |= gb[c - 1] & x.z; gc[c] |= gc[c - 1] & x.w;
+					ha[c] |= ha[c - 1] & y.y; hb[c] |= hb[c - 1] & y.z; hc[c] |= hc[c - 1] & y.w;
+				}
+				ga[0] |= x.y; gb[0] |= x.z; gc[0] |= x.w; ha[0] |= y.y; hb[0] |= y.z; hc[0] |= y.w;
+			}
+			m[0] = ga[CREQ - 1]; m[1] = gb[CREQ - 1]; m[2] = gc[CREQ - 1]; m[3] = ha[CREQ - 1]; m[4] = hb[CREQ - 1]; m[5] = hc[CREQ - 1];
+		}
+		uint32_t left = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]) + __popc(m[5]);
+		SV_TICKW(0);
+		// rounds: every lane pushes up to `quota` of its blocks, then the queue is drained down to less than a warp's worth.
+		// The usual case is one round that takes everything (a sparse sieve); dense phases (c = 1) go 4 blocks per lane a time.
+#pragma unroll 1
+		while (__any_sync(0xffffffffu, left != 0)) {
+			uint32_t inc = left;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+			uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+			uint32_t cnt = left;
+			if (qn + tot > SV_WQCAP) {
+				cnt = min(left, 4u);
+				inc = cnt;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+				tot = __shfl_sync(0xffffffffu, inc, 31);
+			}
+			uint32_t at = qn + inc - cnt;
+			left -= cnt;
+			nc += cnt;
+#pragma unroll
+			for (int wd = 0; wd < 6; ++wd) {
+				const uint32_t b0 = (wd < 3 ? gA : gB) * SIEVE_GROUP_BLOCKS + (wd % 3) * 32;
+#pragma unroll 1
+				while (m[wd] && cnt) { wq[at++] = b0 + (__ffs(m[wd]) - 1); m[wd] &= m[wd] - 1; --cnt; }
+			}
+			qn += tot;
+			__syncwarp();
+			SV_TICKW(1);
+#pragma unroll 1
+			while (qn >= 32) {
+				qn -= 32;
+				const uint32_t blk = wq[qn + lane];
+				__syncwarp();
+				np += resolve_block(sh, blk, onlyCount, tau);
+			}
+			SV_TICKW(2);
+		}
+	}
+	if (qn) {
+		const uint32_t blk = (uint32_t)lane < qn ? wq[lane] : INF;
+		if (blk != INF) np += resolve_block(sh, blk, onlyCount, tau);
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) { nc += __shfl_xor_sync(0xffffffffu, nc, o); np += __shfl_xor_sync(0xffffffffu, np, o); }
+	if (lane == 0) { atomicAdd(&sh.nCand, nc); atomicAdd(&sh.nProbe, np); }
+}
+
+__device__ __forceinline__ void sieve_dispatch(SieveShared& sh, uint32_t creq, uint32_t g0, uint32_t g1, uint32_t nS, uint32_t onlyCount)
+{
+	// thresholds without an instantiation of their own use the next lower one: a superset of the blocks, RESOLVE counts exactly
+	if (creq <= 1) sieve_groups<1>(sh, g0, g1, nS, onlyCount);
+	else if (creq == 2) sieve_groups<2>(sh, g0, g1, nS, onlyCount);
+	else if (creq == 3) sieve_groups<3>(sh, g0, g1, nS, onlyCount);
+	else if (creq < 6) sieve_groups<4>(sh, g0, g1, nS, onlyCount);
+	else if (creq < 8) sieve_groups<6>(sh, g0, g1, nS, onlyCount);
+	else sieve_groups<8>(sh, g0, g1, nS, onlyCount);
 }
 
 // expected candidate blocks per bitmap word when a block needs >= c of K lists, every list setting a block with probability p
@@ -279,7 +356,7 @@ __device__ float sieve_rate(uint32_t K, uint32_t c, float p)
 }
 
 template <class U>
-__global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, const QDesc* __restrict__ desc, const U* __restrict__ qnorm,
+__global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexView ix, const QDesc* __restrict__ desc, const U* __restrict__ qnorm,
                                                              const uint32_t* __restrict__ fastList, uint32_t* __restrict__ counters,
                                                              uint32_t* __restrict__ handList, uint32_t limit, uint32_t outStride,
                                                              uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
@@ -309,6 +386,9 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 		__syncthreads();
 		const uint32_t wi = sh.query;
 		if (wi >= nFast) break;
+#if SV_TIMING
+		long long tick = clock64();
+#endif
 		const uint32_t q = fastList[wi];
 		const QDesc& d = desc[q];
 		if (!(d.flags & 4u)) {                          // not for this kernel: k_fast_search takes it
@@ -348,6 +428,7 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 		}
 		if (tid == 0) {
 			sh.bufCount = 0; sh.overflow = 0; sh.tau = ~0ull; sh.done = 0; sh.nProbe = 0;
+			sh.tim[0] = sh.tim[1] = sh.tim[2] = sh.tim[3] = 0;
 			sh.qlen = d.qlen; sh.nGrams = nGrams; sh.cmin = d.cmin; sh.cprom = d.cprom; sh.nLists = nLists;
 			sh.classMode = classMode;
 			sh.promotedKey = classMode ? 0u : ~float_to_ordered(100.0f);
@@ -389,6 +470,7 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 			const uint32_t onlyCount = (twoPhase && phase == 1) ? 1u : 0u;
 			uint32_t gLo = 0, lastG1 = 0;
 			uint32_t lastCreq = 0, lastLen = 0, lastCands = 0, forceLen = 0;
+			SV_TICK(0);
 			while (gLo < NG) {
 				__syncthreads();                      // the previous pass is complete (its counters and plan have been read)
 				// ---- warp 0: tau from the counts of the pass just finished, the count a term needs from here on, the next pass
@@ -439,19 +521,23 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 					}
 				}
 				__syncthreads();
+				SV_TICK(1);
 				if (sh.done) break;
 				const uint32_t w0 = sh.passG0, w1 = sh.passG1, creq = sh.cRej + 1;
 				if (tid == 0) atomicAdd(&counters[24], 1u);
-				// ---- sieve
-				sieve_dispatch(sh, creq, w0, w1, nSieve);
+				// ---- sieve + resolve, then the blocks left to the general resolution, then what was deferred
+				sieve_dispatch(sh, creq, w0, w1, nSieve, onlyCount);
 				__syncthreads();
+				SV_TICK(2);
 				const uint32_t nCand = sh.nCand;
-				bool redo = nCand > SV_CCAP;
-				uint32_t shorter = redo ? (uint32_t)((float)(w1 - w0) * 0.5f * (float)SV_CCAP / (float)nCand) : 0u;
-				if (!redo) {
-					// ---- resolve the queued blocks, evaluate what was deferred
-					resolve_stage(sh, nCand, nLists, onlyCount);
-					__syncthreads();
+				bool redo = false;
+				uint32_t shorter = 0;
+				{
+					{
+						const uint32_t nSlow = min(sh.nSlow, (uint32_t)SV_SLOWCAP);
+						for (uint32_t i = tid; i < nSlow; i += SV_THREADS) resolve_slow(sh, sh.slowQ[i], onlyCount, sh.tau);
+						if (nSlow) __syncthreads();
+					}
 					if (sh.overflow == 0) {
 						const uint32_t nd = sh.defCount;
 						for (uint32_t i = tid; i < nd; i += SV_THREADS) {
@@ -479,6 +565,7 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 					continue;
 				}
 				forceLen = 0;
+				SV_TICK(3);
 				if (tid == 0) { atomicAdd(&counters[26], nCand); }
 				lastCreq = creq; lastLen = w1 - w0; lastCands = nCand + 1;
 				gLo = w1; lastG1 = w1;
@@ -490,6 +577,7 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 					select_smallest<SV_THREADS>(sh, level, k); level = k; tauReal = true;
 					selectAt = bufCap / 2;
 				}
+				SV_TICK(4);
 			}
 		}
 		if (failed) {
@@ -521,6 +609,10 @@ __global__ void __launch_bounds__(SV_THREADS, 6) k_sieve_search(IndexView ix, co
 			atomicAdd(&counters[25], sh.nProbe);
 			if (level != outStride) atomicAdd(&counters[22], 1u);
 		}
+		SV_TICK(5);
+#if SV_TIMING
+		if (tid == 0) { atomicAdd(&counters[40], sh.tim[0]); atomicAdd(&counters[41], sh.tim[1]); atomicAdd(&counters[42], sh.tim[2]); }
+#endif
 	}
 }
 
