@@ -16,11 +16,13 @@ const char* ssb_last_error(void);
 uint64_t ssb_kernel_launches(void);
 /* binds the engine to a CUDA device (default: current device). Call once per process, before any index. */
 int ssb_set_device(int device);
-/* which kernel answers the batched fast path first: 1 = k_sieve_search (block bitmaps over the posting lists; reads only
- * the postings of blocks that can still matter and hands queries it does not take to k_fast_search), 0 = k_fast_search
- * alone (register K-way merge of the posting lists), -1 = the default (1, or 0 when the environment variable SSB_MERGE
- * is set). Results are identical; the switch exists for measurements and for the parity tests that cover both.
- * 0 on success. */
+/* which kernels answer the batched fast path: 2 = the tile pipeline first (k_tile_plan / k_tile_sieve / k_tile_final: the
+ * sieve below, cut into tiles of a pass so that a batch is balanced tile by tile; hands what it does not take to
+ * k_sieve_search), 1 = k_sieve_search first (block bitmaps over the posting lists; one CTA per query; reads only the
+ * postings of blocks that can still matter and hands queries it does not take to k_fast_search), 0 = k_fast_search alone
+ * (register K-way merge of the posting lists), -1 = the default (2 for batches of >= 128 queries on identity indexes with
+ * >= 400 000 terms, else 1; 0 when the environment variable SSB_MERGE is set, 1 with SSB_NO_TILES). Results are
+ * identical; the switch exists for measurements and for the parity tests, which cover all three. 0 on success. */
 int ssb_set_search_path(int path);
 
 /* ---- index build: replaces StringIndex::StringIndex (nGramSearch.hpp:120-172) ----
@@ -81,9 +83,10 @@ void ssb_search_one_stats(const ssb_index* ix, uint64_t out[2]);   /* [0] calls,
 int ssb_search_batch_device(ssb_index* ix, const void* const* queries, uint32_t nq, float threshold, uint32_t limit);
 
 /* re-runs the device part of the last uploaded batch (queries resident in HBM, results left in HBM);
- * ms[0] = whole device part, ms[1] = k_sieve_search + k_fast_search alone (CUDA events on the engine's stream).
+ * ms[0] = whole device part, ms[1] = the search kernels alone: tile pipeline + k_sieve_search + k_fast_search (CUDA events on
+ * the engine's stream).
  * stats[]: 0 nFast 1 nDense 2 nOverflow 3 postings touched by fast queries 4 answered by k_sieve_search
- *          5 handed from k_sieve_search to k_fast_search 6 of those, given up mid-query 7 reserved */
+ *          5 handed from k_sieve_search to k_fast_search 6 of those, given up mid-query 7 answered by the tile pipeline */
 int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uint32_t limit, float ms[2], uint64_t stats[8]);
 
 /* ---- multi-GPU (key-range shards, one process per GPU): fixed-size per-query records for an all-gather ----

@@ -411,7 +411,7 @@ SSB_API const char* ssb_last_error(void) { return g_lastError; }
 SSB_API uint64_t ssb_kernel_launches(void) { return g_kernel_launches.load(); }
 SSB_API int ssb_set_search_path(int path)
 {
-	if (path < -1 || path > 1) return -1;
+	if (path < -1 || path > 2) return -1;
 	g_search_path.store(path);
 	return 0;
 }
@@ -712,7 +712,7 @@ SSB_API int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uin
 		if (ms) { ms[0] = st.msDevice; ms[1] = st.msFastKernel; }
 		if (stats) {
 			stats[0] = st.nFast; stats[1] = st.nDense; stats[2] = st.nOverflow; stats[3] = st.postingsTouched;
-			stats[4] = st.nSieve; stats[5] = st.nSieveHandover; stats[6] = st.nSieveGiveUp; stats[7] = 0;
+			stats[4] = st.nSieve; stats[5] = st.nSieveHandover; stats[6] = st.nSieveGiveUp; stats[7] = st.nTile;
 		}
 		return 0;
 	}, -1);

@@ -361,12 +361,15 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
                                                              uint32_t* __restrict__ handList, uint32_t limit, uint32_t outStride,
                                                              uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
                                                              float* __restrict__ outScore, unsigned long long* __restrict__ statCounters,
-                                                             uint32_t bufCap, float threshold, uint32_t defExt, HostOut ho)
+                                                             uint32_t bufCap, float threshold, uint32_t nIdx, uint32_t curIdx, uint32_t defExt,
+                                                             HostOut ho)
 {
+	// nIdx / curIdx: which counters hold this launch's list length and work cursor (every fast query, or the ones the tile
+	// pipeline handed over)
 	extern __shared__ __align__(16) unsigned char sv_smem[];
 	SieveShared& sh = *reinterpret_cast<SieveShared*>(sv_smem);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t nFast = counters[0];
+	const uint32_t nFast = counters[nIdx];
 	const uint32_t k = limit;
 	const uint32_t NG = ix.sieveNGroups;
 	const int shift = ix.sieveShift;
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 
 	while (true) {
 		__syncthreads();
-		if (tid == 0) sh.query = atomicAdd(&counters[2], 1u);
+		if (tid == 0) sh.query = atomicAdd(&counters[curIdx], 1u);
 		__syncthreads();
 		const uint32_t wi = sh.query;
 		if (wi >= nFast) break;

@@ -55,8 +55,8 @@ def check_tables(ix, S):
 
 
 def check_search(ix, S, queries, threshold, limit, o=None):
-    """every batch is answered twice — k_sieve_search first (path 1, the default) and k_fast_search alone (path 0) — and
-    both must equal the oracle bit for bit"""
+    """every batch is answered three times — the tile pipeline first (path 2), k_sieve_search first (path 1) and
+    k_fast_search alone (path 0) — and all must equal the oracle bit for bit"""
     import stringsearchlib_b200 as m
     o = o or S.tables()
     counts, ext, sc = S.search_batch(queries, threshold, limit)
@@ -64,7 +64,7 @@ def check_search(ix, S, queries, threshold, limit, o=None):
     kid_of_ext = o["kidOfExt"]
     r = None
     try:
-        for path in (1, 0):
+        for path in (2, 1, 0):
             m.set_search_path(path)
             r = ix.search_batch(queries, threshold, limit)
             assert len(r) == nq
@@ -471,9 +471,19 @@ def test_properties_full_size(ssb):
         same = sc[:, :-1] == sc[:, 1:]
         assert np.all(kid[:, :-1][same] < kid[:, 1:][same])          # ties: kid ascending
         ms, msk, st = ix.search_resident(nq, 0.0, 100)
-        # the default path: k_sieve_search answers (nearly) everything itself
+        # the default path at this size: the tile pipeline answers (nearly) everything itself
         assert st["nFast"] == nq and st["nDense"] == 0 and st["nOverflow"] == 0, st
-        assert st["nSieve"] + st["nSieveHandover"] == nq and st["nSieve"] > nq // 2, st
+        assert st["nTile"] + st["nSieve"] + st["nSieveHandover"] == nq and st["nTile"] > nq // 2, st
+        # k_sieve_search first (one CTA per query) must answer the batch identically
+        try:
+            ssb.set_search_path(1)
+            r4 = ix.search_batch(q, 0.0, 100)
+            _, _, st4 = ix.search_resident(nq, 0.0, 100)
+        finally:
+            ssb.set_search_path(-1)
+        assert np.array_equal(r1.offsets, r4.offsets) and np.array_equal(r1.kids, r4.kids)
+        assert np.array_equal(r1.scores.view(np.uint32), r4.scores.view(np.uint32))
+        assert st4["nTile"] == 0 and st4["nSieve"] + st4["nSieveHandover"] == nq and st4["nSieve"] > nq // 2, st4
         # k_fast_search alone (the register merge) must answer the batch identically
         try:
             ssb.set_search_path(0)
@@ -483,7 +493,7 @@ def test_properties_full_size(ssb):
             ssb.set_search_path(-1)
         assert np.array_equal(r1.offsets, r3.offsets) and np.array_equal(r1.kids, r3.kids)
         assert np.array_equal(r1.scores.view(np.uint32), r3.scores.view(np.uint32))
-        assert st3["nSieve"] == 0 and st3["nFast"] == nq and st3["nDense"] == 0, st3
+        assert st3["nSieve"] == 0 and st3["nTile"] == 0 and st3["nFast"] == nq and st3["nDense"] == 0, st3
         exact = ix.search_batch(keys.slice(1000, 1064), 0.0, 5, strings=True)
         for i in range(64):
             assert exact.query(i)[3][0] == keys.get(1000 + i)
