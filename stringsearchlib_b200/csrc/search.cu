@@ -541,7 +541,7 @@ void ensure_workspace(SearchWorkspace& ws, uint32_t nq, size_t charBytes, uint32
 	if (!ws.ev0) {
 		SSB_CUDA(cudaEventCreate(&ws.ev0)); SSB_CUDA(cudaEventCreate(&ws.ev1));
 		SSB_CUDA(cudaEventCreate(&ws.ev2)); SSB_CUDA(cudaEventCreate(&ws.ev3));
-		ws.counters.alloc(64, s);
+		ws.counters.alloc(512, s);       // [0..63] are copied to the host after every batch; the rest is device-only (tile pipeline)
 		ws.hostCounters.reserve(64);
 	}
 	if (nq > ws.capQ || stride > ws.stride) {
@@ -579,7 +579,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		int numSMs = 0;
 		int ctasFor[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 		int sieveCtas[6] = {0, 0, 0, 0, 0, 0};
-		int tileCtas = 0;
+		int tileCtas = 0, resolveCtas = 0;
 	};
 	static LaunchCfg cfgOf[64];
 	int dev = 0;
@@ -606,7 +606,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		lc.numSMs = n;
 	});
 	const int numSMs = lc.numSMs;
-	int ctasPerSM, sieveCtasPerSM, tileCtasPerSM;
+	int ctasPerSM, sieveCtasPerSM, tileCtasPerSM, resolveCtasPerSM;
 	{
 		std::lock_guard<std::mutex> lk(lc.mu);
 		if (!lc.ctasFor[cfg]) {
@@ -628,15 +628,18 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 				        svBytes, lc.sieveCtas[scfg], SV_THREADS);
 		}
 		if (!lc.tileCtas) {
-			int c = 0;
-			SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_tile_sieve<U>, WT_WARPS * 32, 0));
+			int c = 0, c2 = 0;
+			SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_tile_stream, TS_WARPS * 32, 0));
+			SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_tile_resolve<U>, TS_WARPS * 32, 0));
 			lc.tileCtas = std::max(c, 1);
+			lc.resolveCtas = std::max(c2, 1);
 			if (getenv("SSB_DEBUG"))
-				fprintf(stderr, "[ssb] k_tile_sieve: sizeof(WarpTile)=%zu, %d CTAs/SM x %d warps\n", sizeof(WarpTile), lc.tileCtas, WT_WARPS);
+				fprintf(stderr, "[ssb] k_tile_stream: %d CTAs/SM, k_tile_resolve: %d CTAs/SM (x %d warps)\n", lc.tileCtas, lc.resolveCtas, TS_WARPS);
 		}
 		ctasPerSM = lc.ctasFor[cfg];
 		sieveCtasPerSM = lc.sieveCtas[scfg];
 		tileCtasPerSM = lc.tileCtas;
+		resolveCtasPerSM = lc.resolveCtas;
 	}
 	unsigned long long* statCounters = reinterpret_cast<unsigned long long*>(ws.counters.get() + 8);
 	// tiny batch with pinned result arrays: see k_finalize_tiny (no events: nobody profiles a single query through them)
@@ -678,26 +681,31 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	HostOut ho{};
 	if (direct) { ho.kids = hr->kids; ho.scores = hr->scores; ho.rows = hr->rows; ho.strs = reinterpret_cast<uint64_t*>(hr->strs); ho.strBase = hr->strBase; }
 	if (useTile) {
-		// candidate list per query: 4 * limit rounded up to a power of two within [1024, FS_BUF_MAX] entries
-		uint32_t candCap = 1024;
-		while (candCap < 4 * std::min<uint32_t>(limit, FAST_KLIM) && candCap < (uint32_t)FS_BUF_MAX) candCap <<= 1;
+		// candidate list per query (the final select works on it in shared memory)
+		const uint32_t candCap = (uint32_t)FS_BUF_MAX;
 		const uint32_t NG = v.sieveNGroups;
 		const uint32_t tileG = NG >= 16384 ? 512u : 256u;               // groups per tile (one warp's work: 4-8 steps of 64 groups)
-		const size_t tilesPerRound = (size_t)nq * (NG / tileG + 2);    // a pass is cut into at most ceil(len / tileG) tiles
+		const size_t tilesPerRound = (size_t)nq * (NG / 64 + 2);       // a tile is at least one bitmap step (64 groups) long
 		ws.tileQ.reserve(nq, s);
 		ws.tiles.reserve(tilesPerRound * TP_ROUNDS, s);
 		ws.tileCand.reserve((size_t)nq * candCap, s);
 		ws.fastList3.reserve(nq, s);
 		const unsigned pgrid = grid_for((size_t)nq * 32);
-		const unsigned tgrid = (unsigned)((size_t)numSMs * tileCtasPerSM);
+		const unsigned tgrid = (unsigned)((size_t)numSMs * tileCtasPerSM), rgrid = (unsigned)((size_t)numSMs * resolveCtasPerSM);
+		// record queues of one round: 64 stripes, 1536 records per query overall (a round rarely passes 1000 blocks per query)
+		const uint32_t recCap = (uint32_t)std::max<size_t>(4096, ((size_t)nq * 1536 / TS_STRIPES + 31) & ~size_t(31));
+		ws.tileRecs.reserve((size_t)recCap * TS_STRIPES * 2, s);          // uint4 x 2 per record
 		for (uint32_t r = 0; r <= (uint32_t)TP_ROUNDS; ++r) {
 			uint4* tl = ws.tiles.get() + tilesPerRound * std::min<uint32_t>(r, TP_ROUNDS - 1);
 			k_tile_plan<<<pgrid, 256, 0, s>>>(v, ws.desc.get(), ws.fastList.get(), ws.counters.get(), ws.tileQ.get(), tl, r, limit, tileG,
 			                                  ws.fastList3.get());
 			SSB_LAUNCH_CHECK();
 			if (r == (uint32_t)TP_ROUNDS) break;
-			k_tile_sieve<U><<<tgrid, WT_WARPS * 32, 0, s>>>(v, ws.desc.get(), qn, ws.tileQ.get(), tl, ws.counters.get(), r,
-			                                               ws.tileCand.get(), candCap);
+			k_tile_stream<<<tgrid, TS_WARPS * 32, 0, s>>>(v, ws.desc.get(), ws.tileQ.get(), tl, ws.counters.get(), r,
+			                                              reinterpret_cast<TileRec*>(ws.tileRecs.get()), recCap);
+			SSB_LAUNCH_CHECK();
+			k_tile_resolve<U><<<rgrid, TS_WARPS * 32, 0, s>>>(v, ws.desc.get(), qn, ws.tileQ.get(), reinterpret_cast<const TileRec*>(ws.tileRecs.get()),
+			                                                 recCap, ws.counters.get(), r, ws.tileCand.get(), candCap);
 			SSB_LAUNCH_CHECK();
 		}
 		const size_t finBytes = ((sizeof(FinalShared) + 15) & ~size_t(15)) + (size_t)candCap * 8;
@@ -811,6 +819,10 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 			fprintf(stderr, "[ssb] tile pipeline: %u answered, %u handed to k_sieve_search (%u after a failed tile / out of rounds / too few two-match terms); tiles per round %u %u %u; "
 			        "per answered query %.0f candidate blocks, %.0f probes\n", hc[TP_DONE], hc[TP_HAND], hc[TP_FAILED], hc[TP_COUNT], hc[TP_COUNT + 1],
 			        hc[TP_COUNT + 2], hc[26] / (double)std::max(hc[TP_DONE], 1u), hc[25] / (double)std::max(hc[TP_DONE], 1u));
+		if (dbg && hc[TP_DONE] && hc[33] && !hc[6])
+			fprintf(stderr, "[ssb] k_tile_stream, all rounds, kilocycles per warp (%u warps): tile fetch + set-up %.1f, bitmap steps %.1f, queue pushes %.1f, record rounds %.1f\n",
+			        (unsigned)(numSMs * tileCtasPerSM * TS_WARPS), hc[32] * 0.064 / (numSMs * tileCtasPerSM * TS_WARPS), hc[33] * 0.064 / (numSMs * tileCtasPerSM * TS_WARPS),
+			        hc[34] * 0.064 / (numSMs * tileCtasPerSM * TS_WARPS), hc[35] * 0.064 / (numSMs * tileCtasPerSM * TS_WARPS));
 		if (dbg && hc[6])
 			fprintf(stderr, "[ssb] k_sieve_search per query: %.1f passes (%.2f redone), %.0f candidate blocks, %.0f probes; gave up on %u\n",
 			        hc[24] / (double)hc[6], hc[27] / (double)hc[6], hc[26] / (double)hc[6], hc[25] / (double)hc[6], hc[28]);

@@ -68,7 +68,7 @@ struct SearchWorkspace {
 	                                                              // fastList3: queries the tile pipeline hands to k_sieve_search
 	// tile pipeline (tile_path.cuh): per-query state, the tiles of every round, per-query candidate lists
 	DevBuf<TileQ> tileQ;
-	DevBuf<uint4> tiles;
+	DevBuf<uint4> tiles, tileRecs;
 	DevBuf<unsigned long long> tileCand;
 	// [0]=nFast [1]=nDense [2]=work cursor [3]=overflow count [4]=any out-of-band list [5]=handed to k_fast_search
 	// [6]=answered by k_sieve_search [28]=of [5], given up mid-query [12]=k_fast_search cursor; [8..11] = two u64 statistics;

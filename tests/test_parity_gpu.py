@@ -471,19 +471,20 @@ def test_properties_full_size(ssb):
         same = sc[:, :-1] == sc[:, 1:]
         assert np.all(kid[:, :-1][same] < kid[:, 1:][same])          # ties: kid ascending
         ms, msk, st = ix.search_resident(nq, 0.0, 100)
-        # the default path at this size: the tile pipeline answers (nearly) everything itself
         assert st["nFast"] == nq and st["nDense"] == 0 and st["nOverflow"] == 0, st
-        assert st["nTile"] + st["nSieve"] + st["nSieveHandover"] == nq and st["nTile"] > nq // 2, st
-        # k_sieve_search first (one CTA per query) must answer the batch identically
-        try:
-            ssb.set_search_path(1)
-            r4 = ix.search_batch(q, 0.0, 100)
-            _, _, st4 = ix.search_resident(nq, 0.0, 100)
-        finally:
-            ssb.set_search_path(-1)
-        assert np.array_equal(r1.offsets, r4.offsets) and np.array_equal(r1.kids, r4.kids)
-        assert np.array_equal(r1.scores.view(np.uint32), r4.scores.view(np.uint32))
-        assert st4["nTile"] == 0 and st4["nSieve"] + st4["nSieveHandover"] == nq and st4["nSieve"] > nq // 2, st4
+        assert st["nTile"] + st["nSieve"] + st["nSieveHandover"] == nq, st
+        # each path must answer the batch identically and (nearly) alone: the tile pipeline (2), k_sieve_search (1)
+        for path, key in ((2, "nTile"), (1, "nSieve")):
+            try:
+                ssb.set_search_path(path)
+                r4 = ix.search_batch(q, 0.0, 100)
+                _, _, st4 = ix.search_resident(nq, 0.0, 100)
+            finally:
+                ssb.set_search_path(-1)
+            assert np.array_equal(r1.offsets, r4.offsets) and np.array_equal(r1.kids, r4.kids), path
+            assert np.array_equal(r1.scores.view(np.uint32), r4.scores.view(np.uint32)), path
+            assert st4["nTile"] + st4["nSieve"] + st4["nSieveHandover"] == nq and st4[key] > nq // 2, (path, st4)
+            assert (st4["nTile"] == 0) == (path == 1), (path, st4)
         # k_fast_search alone (the register merge) must answer the batch identically
         try:
             ssb.set_search_path(0)
