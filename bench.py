@@ -443,13 +443,11 @@ def main():
                     "delivery": "N=1: the search kernel stores each finished query straight into the pinned ssb_batch arrays (device-to-host "
                                 "over PCIe, overlapped with the kernel) when every query fills its limit; otherwise compaction + copies"},
             "gpu_launches": int(launches),   # kernels launched in the timed region (each step runs the path twice: e2e + resident)
-            "queries_by_kernel": {"k_tile_sieve": last_st.get("nTile", 0), "k_sieve_search": last_st.get("nSieve", 0),
-                                  "k_fast_search": last_st.get("nFast", 0) - last_st.get("nSieve", 0) - last_st.get("nTile", 0),
+            "queries_by_kernel": {"k_sieve_search": last_st.get("nSieve", 0),
+                                  "k_fast_search": last_st.get("nFast", 0) - last_st.get("nSieve", 0),
                                   "dense": last_st.get("nDense", 0)},
-            "roofline": {"bound": "hbm", "kernel": ("k_tile_sieve" if last_st.get("nTile", 0) * 2 > args.batch else
-                                                    "k_sieve_search" if last_st.get("nSieve", 0) * 2 > args.batch else "k_fast_search"),
-                         "timed": "every search kernel of one batch after query preparation: tile pipeline (k_tile_plan / k_tile_sieve per "
-                                  "round, k_tile_final) + k_sieve_search + k_fast_search (CUDA events on the engine's stream)",
+            "roofline": {"bound": "hbm", "kernel": "k_sieve_search" if last_st.get("nSieve", 0) * 2 > args.batch else "k_fast_search",
+                         "timed": "k_sieve_search + k_fast_search launches of one batch (CUDA events on the engine's stream)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms},

@@ -16,13 +16,11 @@ const char* ssb_last_error(void);
 uint64_t ssb_kernel_launches(void);
 /* binds the engine to a CUDA device (default: current device). Call once per process, before any index. */
 int ssb_set_device(int device);
-/* which kernels answer the batched fast path: 2 = the tile pipeline first (k_tile_plan / k_tile_sieve / k_tile_final: the
- * sieve below, cut into tiles of a pass so that a batch is balanced tile by tile; hands what it does not take to
- * k_sieve_search), 1 = k_sieve_search first (block bitmaps over the posting lists; one CTA per query; reads only the
- * postings of blocks that can still matter and hands queries it does not take to k_fast_search), 0 = k_fast_search alone
- * (register K-way merge of the posting lists), -1 = the default (2 for batches of >= 128 queries on identity indexes with
- * >= 400 000 terms, else 1; 0 when the environment variable SSB_MERGE is set, 1 with SSB_NO_TILES). Results are
- * identical; the switch exists for measurements and for the parity tests, which cover all three. 0 on success. */
+/* which kernel answers the batched fast path first: 1 = k_sieve_search (block bitmaps over the posting lists; reads only
+ * the postings of blocks that can still matter and hands queries it does not take to k_fast_search), 0 = k_fast_search
+ * alone (register K-way merge of the posting lists), -1 = the default (1, or 0 when the environment variable SSB_MERGE
+ * is set). Results are identical; the switch exists for measurements and for the parity tests that cover both.
+ * 0 on success. */
 int ssb_set_search_path(int path);
 
 /* ---- index build: replaces StringIndex::StringIndex (nGramSearch.hpp:120-172) ----
@@ -65,7 +63,11 @@ typedef struct ssb_batch {
 	uint64_t* rows;         /* global first row of the key */
 	const void** strings;   /* NUL-terminated key strings (char or wchar_t), aliasing index storage */
 } ssb_batch;
-/* queries: nq NUL-terminated strings. limit 0 = unlimited. Returns NULL on failure. */
+/* queries: nq NUL-terminated strings. limit 0 = unlimited (nGramSearch.hpp:420-421). Returns NULL on failure.
+ * Cost of large limits: a result list never holds more than K keys, so limit is first clamped to the number of keys; up to
+ * 2048 results per query the batch runs on the fused kernels. Beyond that (limit 0 or > 2048 on an index with more than
+ * 2048 keys) every such query takes the per-query dense path: two memsets over T + K counters, two radix sorts and about
+ * five stream synchronisations per query, serial within the batch — exact, but milliseconds per query on large indexes. */
 ssb_batch* ssb_search_batch(ssb_index* ix, const void* const* queries, uint32_t nq, float threshold, uint32_t limit);
 /* same, from packed units + offsets[nq+1] */
 ssb_batch* ssb_search_batch_packed(ssb_index* ix, const void* units, const uint32_t* offsets, uint32_t nq, float threshold,
@@ -79,14 +81,14 @@ ssb_batch* ssb_search_one(ssb_index* ix, const void* query, float threshold, uin
 void ssb_search_one_stats(const ssb_index* ix, uint64_t out[2]);   /* [0] calls, [1] batches run for them */
 
 /* uploads and answers a batch but leaves the per-shard results in HBM (multi-GPU: they go through ssb_export_records*
- * and the cross-shard merge instead of back to this host). 0 on success. */
+ * and the cross-shard merge instead of back to this host). Lists are cut at min(limit, 2048) results per query here (there
+ * is no out-of-band channel for longer ones). 0 on success. */
 int ssb_search_batch_device(ssb_index* ix, const void* const* queries, uint32_t nq, float threshold, uint32_t limit);
 
 /* re-runs the device part of the last uploaded batch (queries resident in HBM, results left in HBM);
- * ms[0] = whole device part, ms[1] = the search kernels alone: tile pipeline + k_sieve_search + k_fast_search (CUDA events on
- * the engine's stream).
+ * ms[0] = whole device part, ms[1] = k_sieve_search + k_fast_search alone (CUDA events on the engine's stream).
  * stats[]: 0 nFast 1 nDense 2 nOverflow 3 postings touched by fast queries 4 answered by k_sieve_search
- *          5 handed from k_sieve_search to k_fast_search 6 of those, given up mid-query 7 answered by the tile pipeline */
+ *          5 handed from k_sieve_search to k_fast_search 6 of those, given up mid-query 7 reserved */
 int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uint32_t limit, float ms[2], uint64_t stats[8]);
 
 /* ---- multi-GPU (key-range shards, one process per GPU): fixed-size per-query records for an all-gather ----

@@ -1,7 +1,7 @@
 #!/bin/bash
 # one GPU iteration: parity tests, a short bench line, optional ncu capture of the sieve kernel (arg 1 = report name)
 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-SSB_TILES=1 SSB_DEBUG=1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/b1.log 2> gpurun_out/b1.err
+SSB_DEBUG=1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/b1.log 2> gpurun_out/b1.err
 python - <<'PY'
 import json
 d=json.loads(open("gpurun_out/b1.log").read().strip().splitlines()[-1])

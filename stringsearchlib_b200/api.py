@@ -92,10 +92,9 @@ def kernel_launches():
 
 
 def set_search_path(path):
-    """2 = tile pipeline first, 1 = k_sieve_search first, 0 = k_fast_search alone, -1 = default (2 for batches on large identity
-    indexes, else 1; 0 when SSB_MERGE is set); identical results (include/ssb_engine.h)."""
+    """1 = k_sieve_search first, 0 = k_fast_search alone, -1 = default (1 unless SSB_MERGE is set); identical results (include/ssb_engine.h)."""
     if core_library().ssb_set_search_path(int(path)) != 0:
-        raise ValueError("search path must be -1, 0, 1 or 2")
+        raise ValueError("search path must be -1, 0 or 1")
 
 
 def set_device(device):
@@ -349,7 +348,7 @@ class Index:
         if self._lib.ssb_search_resident(self._h, nq, threshold, limit, ms, st) != 0:
             raise RuntimeError(self._lib.ssb_last_error().decode())
         return ms[0], ms[1], dict(nFast=int(st[0]), nDense=int(st[1]), nOverflow=int(st[2]), postings=int(st[3]),
-                                  nSieve=int(st[4]), nSieveHandover=int(st[5]), nSieveGiveUp=int(st[6]), nTile=int(st[7]))
+                                  nSieve=int(st[4]), nSieveHandover=int(st[5]), nSieveGiveUp=int(st[6]))
 
     def export_records_p2p(self, nq, limit, peer_recv, rank):
         """fused export + exchange: query q's records go straight into peer_recv[q // (nq/N)] (peer-mapped pointers)."""

@@ -178,7 +178,8 @@ ssb_index* create_from_pointers(const C* const* words, uint64_t size, uint16_t r
                                 uint64_t rowBase)
 {
 	g_engine.init();
-	auto ix = std::make_unique<ssb_index>();
+	// (ssb_index_destroy, not delete, if the build throws: the stream has to be synchronised and destroyed too)
+	std::unique_ptr<ssb_index, void (*)(ssb_index*)> ix(new ssb_index(), &ssb_index_destroy);
 	default_valid(ix->validLut);
 	SSB_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
 	auto t0 = std::chrono::steady_clock::now();
@@ -238,7 +239,8 @@ ssb_index* create_from_packed(const void* units, const uint64_t* offsets, const 
                               const float* weight, uint16_t gSize, int unitBytes, uint64_t rowBase)
 {
 	g_engine.init();
-	auto ix = std::make_unique<ssb_index>();
+	// (ssb_index_destroy, not delete, if the build throws: the stream has to be synchronised and destroyed too)
+	std::unique_ptr<ssb_index, void (*)(ssb_index*)> ix(new ssb_index(), &ssb_index_destroy);
 	default_valid(ix->validLut);
 	SSB_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
 	PackedWords pw;
@@ -376,11 +378,17 @@ template <class T> void save_buf(FILE* f, const DevBuf<T>& b, size_t count, PinB
 		write_all(f, bounce.get(), len);
 	}
 }
-template <class T> void load_buf(FILE* f, DevBuf<T>& b, PinBuf<uint8_t>& bounce, cudaStream_t s)
+// expect: the element count the header implies, or SIZE_MAX for arrays whose length only the file knows (then the bytes left
+// in the file bound it): a truncated or corrupt file must not turn into a huge allocation or into kernels that index past
+// the end of a short array
+template <class T> void load_buf(FILE* f, DevBuf<T>& b, size_t expect, uint64_t fileBytes, PinBuf<uint8_t>& bounce, cudaStream_t s)
 {
 	uint64_t n = 0;
 	read_all(f, &n, 8);
-	if (n > (1ull << 36)) throw std::runtime_error("ssb_index_load: corrupt array size");
+	const long pos = ftell(f);
+	if (pos < 0 || n > (1ull << 36) || n * sizeof(T) > fileBytes - std::min<uint64_t>(fileBytes, (uint64_t)pos) ||
+	    (expect != SIZE_MAX && n != expect))
+		throw std::runtime_error("ssb_index_load: corrupt or truncated index file (array size)");
 	b.alloc(n, s);
 	const size_t chunk = bounce.size();
 	for (size_t off = 0; off < n * sizeof(T); off += chunk) {
@@ -390,16 +398,17 @@ template <class T> void load_buf(FILE* f, DevBuf<T>& b, PinBuf<uint8_t>& bounce,
 		SSB_CUDA(cudaStreamSynchronize(s));
 	}
 }
-// one visitor keeps the order of the arrays identical for save and load
+// one visitor keeps the order of the arrays identical for save and load; the third argument tells whether the count follows
+// from the header (true) or is the array's own size (false: unknown before the array has been read)
 template <class F> void for_each_array(DeviceIndex& d, F f)
 {
-	f(d.symTable, d.symTable.size()); f(d.validLut, d.validLut.size());
-	f(d.gramCodes, (size_t)d.G); f(d.gramOff, (size_t)d.G + 1); f(d.postings, d.postings.size());
-	f(d.termOff, (size_t)d.T + 1); f(d.termChars, d.termChars.size()); f(d.termEdgeOff, (size_t)d.T + 1);
-	f(d.edgeKid, (size_t)d.E); f(d.edgeW, (size_t)d.E); f(d.shortTerms, (size_t)d.nShort);
-	f(d.keyOff, (size_t)d.K + 1); f(d.keyChars, d.keyChars.size()); f(d.keyEdgeOff, (size_t)d.K + 1);
-	f(d.keyEdgeTerm, (size_t)d.E); f(d.keyEdgeW, (size_t)d.E); f(d.keyWmax, (size_t)d.K); f(d.keyRow, (size_t)d.K);
-	f(d.keyHash, (size_t)d.K);
+	f(d.symTable, d.symTable.size(), false); f(d.validLut, d.validLut.size(), false);
+	f(d.gramCodes, (size_t)d.G, true); f(d.gramOff, (size_t)d.G + 1, true); f(d.postings, d.postings.size(), false);
+	f(d.termOff, (size_t)d.T + 1, true); f(d.termChars, d.termChars.size(), false); f(d.termEdgeOff, (size_t)d.T + 1, true);
+	f(d.edgeKid, (size_t)d.E, true); f(d.edgeW, (size_t)d.E, true); f(d.shortTerms, (size_t)d.nShort, true);
+	f(d.keyOff, (size_t)d.K + 1, true); f(d.keyChars, d.keyChars.size(), false); f(d.keyEdgeOff, (size_t)d.K + 1, true);
+	f(d.keyEdgeTerm, (size_t)d.E, true); f(d.keyEdgeW, (size_t)d.E, true); f(d.keyWmax, (size_t)d.K, true); f(d.keyRow, (size_t)d.K, true);
+	f(d.keyHash, (size_t)d.K, true);
 }
 }   // namespace
 
@@ -411,7 +420,7 @@ SSB_API const char* ssb_last_error(void) { return g_lastError; }
 SSB_API uint64_t ssb_kernel_launches(void) { return g_kernel_launches.load(); }
 SSB_API int ssb_set_search_path(int path)
 {
-	if (path < -1 || path > 2) return -1;
+	if (path < -1 || path > 1) return -1;
 	g_search_path.store(path);
 	return 0;
 }
@@ -455,7 +464,7 @@ SSB_API int ssb_index_save(ssb_index* ix, const char* path)
 		write_all(f.get(), &h, sizeof(h));
 		PinBuf<uint8_t> bounce;
 		bounce.alloc_exact(16u << 20);
-		for_each_array(d, [&](auto& b, size_t count) { save_buf(f.get(), b, count, bounce, ix->stream); });
+		for_each_array(d, [&](auto& b, size_t count, bool) { save_buf(f.get(), b, count, bounce, ix->stream); });
 		write_all(f.get(), ix->hk.chars, ix->hk.charBytes);
 		if (fflush(f.get()) != 0) throw std::runtime_error("ssb_index_save: flush failed");
 		return 0;
@@ -474,7 +483,12 @@ SSB_API ssb_index* ssb_index_load(const char* path)
 		if (memcmp(h.magic, INDEX_MAGIC, 8) != 0 || h.version != 1 || h.headerBytes != sizeof(IndexFileHeader))
 			throw std::runtime_error("ssb_index_load: not an index file of this engine version");
 		if ((h.unit != 1 && h.unit != 4) || h.g < 1 || h.g > MAX_GSIZE) throw std::runtime_error("ssb_index_load: corrupt header");
-		auto ix = std::make_unique<ssb_index>();
+		if (fseek(f.get(), 0, SEEK_END) != 0) throw std::runtime_error("ssb_index_load: cannot seek");
+		const long endPos = ftell(f.get());
+		if (endPos < 0 || fseek(f.get(), (long)sizeof(h), SEEK_SET) != 0) throw std::runtime_error("ssb_index_load: cannot seek");
+		const uint64_t fileBytes = (uint64_t)endPos;
+		// (ssb_index_destroy, not delete: the stream has to be synchronised and destroyed too)
+		std::unique_ptr<ssb_index, void (*)(ssb_index*)> ix(new ssb_index(), &ssb_index_destroy);
 		SSB_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
 		DeviceIndex& d = ix->dix;
 		d.g = h.g; d.unit = h.unit; d.symBits = h.symBits; d.indexed = h.indexed != 0;
@@ -485,7 +499,10 @@ SSB_API ssb_index* ssb_index_load(const char* path)
 		memcpy(ix->validLut, h.validLut, 256);
 		PinBuf<uint8_t> bounce;
 		bounce.alloc_exact(16u << 20);
-		for_each_array(d, [&](auto& b, size_t) { load_buf(f.get(), b, bounce, ix->stream); });
+		for_each_array(d, [&](auto& b, size_t count, bool fromHeader) { load_buf(f.get(), b, fromHeader ? count : SIZE_MAX, fileBytes, bounce, ix->stream); });
+		if (d.postings.size() < (size_t)d.P || d.termChars.size() < (size_t)d.termUnits * d.unit || d.keyChars.size() < (size_t)d.keyUnits * d.unit ||
+		    d.validLut.size() < 256 || h.hostKeyBytes > (uint64_t)d.keyChars.size())
+			throw std::runtime_error("ssb_index_load: corrupt or truncated index file (table sizes)");
 		ix->hk.reset();
 		ix->hk.K = h.K;
 		ix->hk.charBytes = h.hostKeyBytes;
@@ -654,31 +671,41 @@ SSB_API ssb_batch* ssb_search_one(ssb_index* ix, const void* query, float thresh
 	ix->onePending.push_back(&me);
 	while (!me.done) {
 		if (ix->oneBusy) { ix->oneCv.wait(lk); continue; }
-		// leader: everything pending with my parameters (my own request included) goes into one batch
+		// leader: everything pending with my parameters goes into one batch — my own request always (thresholds are compared
+		// bit for bit: a NaN threshold still matches itself)
 		ix->oneBusy = true;
 		std::vector<ssb_index::OneReq*> mine, rest;
-		for (auto* r : ix->onePending) ((r->th == me.th && r->limit == me.limit) ? mine : rest).push_back(r);
+		for (auto* r : ix->onePending)
+			((r == &me || (memcmp(&r->th, &me.th, sizeof(float)) == 0 && r->limit == me.limit)) ? mine : rest).push_back(r);
 		ix->onePending.swap(rest);
 		lk.unlock();
-		std::vector<const void*> qs(mine.size());
-		for (size_t i = 0; i < mine.size(); ++i) qs[i] = mine[i]->q;
-		ssb_batch* b = ssb_search_batch(ix, qs.data(), (uint32_t)qs.size(), threshold, limit);
-		ix->oneBatches.fetch_add(1, std::memory_order_relaxed);
-		if (b && mine.size() == 1) mine[0]->out = b;
-		else if (b) {
-			for (size_t i = 0; i < mine.size(); ++i) {             // hand every caller its own slice (heap arrays, like marshal())
-				const uint32_t o = b->offsets[i], n = b->offsets[i + 1] - o;
-				auto* impl = new BatchImpl();
-				ssb_batch* s = &impl->pub;
-				s->nq = 1;
-				s->offsets = new uint32_t[2]{0, n};
-				s->kids = new uint32_t[n ? n : 1]; s->scores = new float[n ? n : 1];
-				s->rows = new uint64_t[n ? n : 1]; s->strings = new const void*[n ? n : 1];
-				memcpy(s->kids, b->kids + o, (size_t)n * 4); memcpy(s->scores, b->scores + o, (size_t)n * 4);
-				memcpy(s->rows, b->rows + o, (size_t)n * 8); memcpy(s->strings, b->strings + o, (size_t)n * sizeof(void*));
-				mine[i]->out = s;
+		// whatever happens below, every request of this batch is marked done and the index is released: a caller left
+		// waiting would wait forever (out stays nullptr on failure, which is this function's error value)
+		try {
+			std::vector<const void*> qs(mine.size());
+			for (size_t i = 0; i < mine.size(); ++i) qs[i] = mine[i]->q;
+			ssb_batch* b = ssb_search_batch(ix, qs.data(), (uint32_t)qs.size(), threshold, limit);
+			ix->oneBatches.fetch_add(1, std::memory_order_relaxed);
+			if (b && mine.size() == 1) mine[0]->out = b;
+			else if (b) {
+				for (size_t i = 0; i < mine.size(); ++i) {             // hand every caller its own slice (heap arrays, like marshal())
+					const uint32_t o = b->offsets[i], n = b->offsets[i + 1] - o;
+					auto* impl = new BatchImpl();
+					ssb_batch* s = &impl->pub;
+					mine[i]->out = s;                                  // owned from here on: ssb_batch_free copes with partly filled slices
+					s->nq = 1;
+					s->offsets = new uint32_t[2]{0, n};
+					s->kids = new uint32_t[n ? n : 1]; s->scores = new float[n ? n : 1];
+					s->rows = new uint64_t[n ? n : 1]; s->strings = new const void*[n ? n : 1];
+					memcpy(s->kids, b->kids + o, (size_t)n * 4); memcpy(s->scores, b->scores + o, (size_t)n * 4);
+					memcpy(s->rows, b->rows + o, (size_t)n * 8); memcpy(s->strings, b->strings + o, (size_t)n * sizeof(void*));
+				}
+				ssb_batch_free(b);
 			}
-			ssb_batch_free(b);
+		} catch (const std::exception& e) {
+			set_last_error(e.what());
+		} catch (...) {
+			set_last_error("ssb_search_one: unknown error");
 		}
 		lk.lock();
 		for (auto* r : mine) r->done = true;
@@ -712,7 +739,7 @@ SSB_API int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uin
 		if (ms) { ms[0] = st.msDevice; ms[1] = st.msFastKernel; }
 		if (stats) {
 			stats[0] = st.nFast; stats[1] = st.nDense; stats[2] = st.nOverflow; stats[3] = st.postingsTouched;
-			stats[4] = st.nSieve; stats[5] = st.nSieveHandover; stats[6] = st.nSieveGiveUp; stats[7] = st.nTile;
+			stats[4] = st.nSieve; stats[5] = st.nSieveHandover; stats[6] = st.nSieveGiveUp; stats[7] = 0;
 		}
 		return 0;
 	}, -1);

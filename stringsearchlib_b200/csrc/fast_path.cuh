@@ -203,6 +203,22 @@ __device__ void select_smallest(SH& sh, uint32_t n, uint32_t k)
 template <int NT, int BAR = 0, class SH>
 __device__ void sort_buffer(SH& sh, uint32_t n)
 {
+	if (n <= 2u * NT) {
+		// short lists (the usual top-100): every thread ranks its (at most two) entries against all others — the entries are
+		// distinct, so the rank is the position — two barriers instead of one per bitonic stage
+		const uint32_t i0 = threadIdx.x, i1 = threadIdx.x + NT;
+		const unsigned long long k0 = i0 < n ? sh.buf[i0] : ~0ull, k1 = i1 < n ? sh.buf[i1] : ~0ull;
+		uint32_t r0 = 0, r1 = 0;
+		for (uint32_t j = 0; j < n; ++j) {
+			const unsigned long long v = sh.buf[j];
+			r0 += v < k0; r1 += v < k1;
+		}
+		group_sync<BAR, NT>();
+		if (i0 < n) sh.buf[r0] = k0;
+		if (i1 < n) sh.buf[r1] = k1;
+		group_sync<BAR, NT>();
+		return;
+	}
 	uint32_t p = 1;
 	while (p < n) p <<= 1;
 	for (uint32_t i = n + threadIdx.x; i < p; i += NT) sh.buf[i] = ~0ull;

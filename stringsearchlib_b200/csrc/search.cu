@@ -244,7 +244,6 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 
 #include "fast_path.cuh"   // k_fast_search (inside namespace ssb)
 #include "sieve_path.cuh"  // k_sieve_search
-#include "tile_path.cuh"   // k_tile_plan / k_tile_sieve / k_tile_final
 
 namespace {
 
@@ -528,6 +527,13 @@ void run_dense_query(const DeviceIndex& ix, const IndexView& v, SearchWorkspace&
 			std::vector<std::pair<uint32_t, float>> lst(take);
 			for (uint32_t i = 0; i < take; ++i) lst[i] = {hkid[i], hsc[i]};
 			out->big.emplace_back(q, std::move(lst));
+		} else {
+			// device-only / resident callers (key-range shards, kernel timing) have no out-of-band channel: they get the
+			// first `stride` results of the list (limit clamped to FAST_KLIM, include/ssb_engine.h) instead of none
+			k_dense_emit<<<grid_for(stride), 256, 0, s>>>(sorted, stride, ws.outKid.get() + (size_t)q * stride, ws.outScore.get() + (size_t)q * stride);
+			SSB_LAUNCH_CHECK();
+			SSB_CUDA(cudaMemcpyAsync(ws.outCount.get() + q, &stride, 4, cudaMemcpyHostToDevice, s));
+			SSB_CUDA(cudaStreamSynchronize(s));   // `stride` lives on this stack frame
 		}
 	} else {
 		uint32_t zero = 0;
@@ -541,7 +547,7 @@ void ensure_workspace(SearchWorkspace& ws, uint32_t nq, size_t charBytes, uint32
 	if (!ws.ev0) {
 		SSB_CUDA(cudaEventCreate(&ws.ev0)); SSB_CUDA(cudaEventCreate(&ws.ev1));
 		SSB_CUDA(cudaEventCreate(&ws.ev2)); SSB_CUDA(cudaEventCreate(&ws.ev3));
-		ws.counters.alloc(512, s);       // [0..63] are copied to the host after every batch; the rest is device-only (tile pipeline)
+		ws.counters.alloc(64, s);
 		ws.hostCounters.reserve(64);
 	}
 	if (nq > ws.capQ || stride > ws.stride) {
@@ -579,7 +585,6 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		int numSMs = 0;
 		int ctasFor[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 		int sieveCtas[6] = {0, 0, 0, 0, 0, 0};
-		int tileCtas = 0, resolveCtas = 0;
 	};
 	static LaunchCfg cfgOf[64];
 	int dev = 0;
@@ -600,13 +605,11 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		const int maxSv = (int)(((sizeof(SieveShared) + 15) & ~size_t(15)) + (size_t)FS_BUF_MAX * 8 + (size_t)FS_DEF_EXT * 8);
 		SSB_CUDA(cudaFuncSetAttribute(k_sieve_search<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSv));
 		SSB_CUDA(cudaFuncSetAttribute(k_sieve_search<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSv));
-		SSB_CUDA(cudaFuncSetAttribute(k_tile_final, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                              (int)(((sizeof(FinalShared) + 15) & ~size_t(15)) + (size_t)FS_BUF_MAX * 8)));
 		SSB_CUDA(cudaFuncSetAttribute(k_order_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ORDER_MAX * 8)));
 		lc.numSMs = n;
 	});
 	const int numSMs = lc.numSMs;
-	int ctasPerSM, sieveCtasPerSM, tileCtasPerSM, resolveCtasPerSM;
+	int ctasPerSM, sieveCtasPerSM;
 	{
 		std::lock_guard<std::mutex> lk(lc.mu);
 		if (!lc.ctasFor[cfg]) {
@@ -627,19 +630,8 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 				fprintf(stderr, "[ssb] k_sieve_search: sizeof(SieveShared)=%zu, dynamic smem=%zu B, %d CTAs/SM x %d threads\n", sizeof(SieveShared),
 				        svBytes, lc.sieveCtas[scfg], SV_THREADS);
 		}
-		if (!lc.tileCtas) {
-			int c = 0, c2 = 0;
-			SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_tile_stream, TS_WARPS * 32, 0));
-			SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_tile_resolve<U>, TS_WARPS * 32, 0));
-			lc.tileCtas = std::max(c, 1);
-			lc.resolveCtas = std::max(c2, 1);
-			if (getenv("SSB_DEBUG"))
-				fprintf(stderr, "[ssb] k_tile_stream: %d CTAs/SM, k_tile_resolve: %d CTAs/SM (x %d warps)\n", lc.tileCtas, lc.resolveCtas, TS_WARPS);
-		}
 		ctasPerSM = lc.ctasFor[cfg];
 		sieveCtasPerSM = lc.sieveCtas[scfg];
-		tileCtasPerSM = lc.tileCtas;
-		resolveCtasPerSM = lc.resolveCtas;
 	}
 	unsigned long long* statCounters = reinterpret_cast<unsigned long long*>(ws.counters.get() + 8);
 	// tiny batch with pinned result arrays: see k_finalize_tiny (no events: nobody profiles a single query through them)
@@ -652,20 +644,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	                                                          ws.fastList.get(), ws.denseList.get(), ws.counters.get(),
 	                                                          ws.outCount.get());
 	SSB_LAUNCH_CHECK();
-	// Which kernels answer the fast queries (all exact, the parity tests run every batch through each):
-	//   2  the tile pipeline first (k_tile_plan / k_tile_sieve / k_tile_final), what it hands over -> k_sieve_search -> k_fast_search
-	//   1  k_sieve_search first, what it hands over -> k_fast_search
-	//   0  k_fast_search alone
-	//  -1  default: 2 for batches on large identity indexes (where a batch is worth ten more launches), else 1; 0 with SSB_MERGE
-	constexpr bool TILE_DEFAULT = false;     // the pipeline is opt-in (path 2 / SSB_TILES) until it beats k_sieve_search
-	static const int envPath = getenv("SSB_MERGE") ? 0 : (getenv("SSB_NO_TILES") ? 1 : (getenv("SSB_TILES") ? 2 : -1));
-	int pathOpt = g_search_path.load(std::memory_order_relaxed);
-	if (pathOpt < 0) pathOpt = envPath;
-	const bool classIndex = ix.identity && ix.uniformW;
-	if (pathOpt < 0) pathOpt = (TILE_DEFAULT && classIndex && v.sieveNGroups != 0 && nq >= 128 && ix.T >= 400000u) ? 2 : 1;
-	const bool useSieve = pathOpt >= 1 && v.sieveNGroups != 0;
-	const bool useTile = pathOpt == 2 && useSieve && classIndex && !tiny;
-	if (!useTile && nq >= 256 && nq <= ORDER_MAX) {      // a handful of queries gain nothing from LPT order; tiles need none
+	if (nq >= 256 && nq <= ORDER_MAX) {      // a handful of queries gain nothing from LPT order
 		k_order_fast<<<1, 1024, ORDER_MAX * 8, s>>>(ws.desc.get(), ws.fastList.get(), ws.counters.get());
 		SSB_LAUNCH_CHECK();
 	}
@@ -674,51 +653,21 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	// queries first and hands the ones it does not take (a list without bitmap, > 16 lists, edit-distance path) or cannot finish
 	// to k_fast_search through fastList2. ssb_set_search_path(0) / SSB_MERGE=1: k_fast_search answers everything (the parity tests
 	// run every batch both ways).
+	static const int envPath = getenv("SSB_MERGE") ? 0 : 1;
+	int pathOpt = g_search_path.load(std::memory_order_relaxed);
+	if (pathOpt < 0) pathOpt = envPath;
+	const bool useSieve = pathOpt == 1 && v.sieveNGroups != 0;
 	// direct delivery (see HostOut): possible when the caller gave pinned CSR arrays, the stride is the limit itself and only
 	// k_fast_search writes results; it holds if every query turns out to fill its `limit` slots (checked after the kernel)
 	const bool direct = !tiny && hr && ix.K && hr->capQ >= nq && hr->capResults >= (size_t)nq * stride && stride == limit &&
 	                    (size_t)nq * stride < (1ull << 32);
 	HostOut ho{};
 	if (direct) { ho.kids = hr->kids; ho.scores = hr->scores; ho.rows = hr->rows; ho.strs = reinterpret_cast<uint64_t*>(hr->strs); ho.strBase = hr->strBase; }
-	if (useTile) {
-		// candidate list per query (the final select works on it in shared memory)
-		const uint32_t candCap = (uint32_t)FS_BUF_MAX;
-		const uint32_t NG = v.sieveNGroups;
-		const uint32_t tileG = NG >= 16384 ? 512u : 256u;               // groups per tile (one warp's work: 4-8 steps of 64 groups)
-		const size_t tilesPerRound = (size_t)nq * (NG / 64 + 2);       // a tile is at least one bitmap step (64 groups) long
-		ws.tileQ.reserve(nq, s);
-		ws.tiles.reserve(tilesPerRound * TP_ROUNDS, s);
-		ws.tileCand.reserve((size_t)nq * candCap, s);
-		ws.fastList3.reserve(nq, s);
-		const unsigned pgrid = grid_for((size_t)nq * 32);
-		const unsigned tgrid = (unsigned)((size_t)numSMs * tileCtasPerSM), rgrid = (unsigned)((size_t)numSMs * resolveCtasPerSM);
-		// record queues of one round: 64 stripes, 1536 records per query overall (a round rarely passes 1000 blocks per query)
-		const uint32_t recCap = (uint32_t)std::max<size_t>(4096, ((size_t)nq * 1536 / TS_STRIPES + 31) & ~size_t(31));
-		ws.tileRecs.reserve((size_t)recCap * TS_STRIPES * 2, s);          // uint4 x 2 per record
-		for (uint32_t r = 0; r <= (uint32_t)TP_ROUNDS; ++r) {
-			uint4* tl = ws.tiles.get() + tilesPerRound * std::min<uint32_t>(r, TP_ROUNDS - 1);
-			k_tile_plan<<<pgrid, 256, 0, s>>>(v, ws.desc.get(), ws.fastList.get(), ws.counters.get(), ws.tileQ.get(), tl, r, limit, tileG,
-			                                  ws.fastList3.get());
-			SSB_LAUNCH_CHECK();
-			if (r == (uint32_t)TP_ROUNDS) break;
-			k_tile_stream<<<tgrid, TS_WARPS * 32, 0, s>>>(v, ws.desc.get(), ws.tileQ.get(), tl, ws.counters.get(), r,
-			                                              reinterpret_cast<TileRec*>(ws.tileRecs.get()), recCap);
-			SSB_LAUNCH_CHECK();
-			k_tile_resolve<U><<<rgrid, TS_WARPS * 32, 0, s>>>(v, ws.desc.get(), qn, ws.tileQ.get(), reinterpret_cast<const TileRec*>(ws.tileRecs.get()),
-			                                                 recCap, ws.counters.get(), r, ws.tileCand.get(), candCap);
-			SSB_LAUNCH_CHECK();
-		}
-		const size_t finBytes = ((sizeof(FinalShared) + 15) & ~size_t(15)) + (size_t)candCap * 8;
-		k_tile_final<<<nq, 128, finBytes, s>>>(v, ws.desc.get(), ws.fastList.get(), ws.counters.get(), ws.tileQ.get(), ws.tileCand.get(), candCap,
-		                                       limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(), statCounters, ho);
-		SSB_LAUNCH_CHECK();
-	}
 	if (useSieve) {
 		const unsigned sgrid = (unsigned)std::min<size_t>((size_t)numSMs * sieveCtasPerSM, std::max<uint32_t>(nq, 1));
-		k_sieve_search<U><<<sgrid, SV_THREADS, svBytes, s>>>(v, ws.desc.get(), qn, useTile ? ws.fastList3.get() : ws.fastList.get(),
-		                                                    ws.counters.get(), ws.fastList2.get(), limit, stride, ws.outCount.get(),
-		                                                    ws.outKid.get(), ws.outScore.get(), statCounters, bufCap, threshold,
-		                                                    useTile ? TP_HAND : 0u, useTile ? TP_SVCUR : 2u, defExt, ho);
+		k_sieve_search<U><<<sgrid, SV_THREADS, svBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(), ws.fastList2.get(),
+		                                                    limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(),
+		                                                    statCounters, bufCap, threshold, defExt, ho);
 		SSB_LAUNCH_CHECK();
 	}
 	const uint32_t* fl = useSieve ? ws.fastList2.get() : ws.fastList.get();
@@ -810,19 +759,10 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	if (st) {
 		st->nFast = nFast; st->nDense = nDense; st->nOverflow = nOverflow;
 		st->nSieve = hc[6]; st->nSieveHandover = hc[5]; st->nSieveGiveUp = hc[28];
-		st->nTile = hc[TP_DONE]; st->nTileHandover = hc[TP_HAND];
 		static const bool dbg = getenv("SSB_DEBUG") != nullptr;
 		if (dbg && nFast)
 			fprintf(stderr, "[ssb] k_fast_search per query: %.1f passes, %.2f redone, %.1f selects, %.1f deferred evaluations\n", hc[16] / (double)nFast,
 			        hc[17] / (double)nFast, hc[18] / (double)nFast, hc[19] / (double)nFast);
-		if (dbg && hc[TP_DONE] + hc[TP_HAND])
-			fprintf(stderr, "[ssb] tile pipeline: %u answered, %u handed to k_sieve_search (%u after a failed tile / out of rounds / too few two-match terms); tiles per round %u %u %u; "
-			        "per answered query %.0f candidate blocks, %.0f probes\n", hc[TP_DONE], hc[TP_HAND], hc[TP_FAILED], hc[TP_COUNT], hc[TP_COUNT + 1],
-			        hc[TP_COUNT + 2], hc[26] / (double)std::max(hc[TP_DONE], 1u), hc[25] / (double)std::max(hc[TP_DONE], 1u));
-		if (dbg && hc[TP_DONE] && hc[33] && !hc[6])
-			fprintf(stderr, "[ssb] k_tile_stream, all rounds, kilocycles per warp (%u warps): tile fetch + set-up %.1f, bitmap steps %.1f, queue pushes %.1f, record rounds %.1f\n",
-			        (unsigned)(numSMs * tileCtasPerSM * TS_WARPS), hc[32] * 0.064 / (numSMs * tileCtasPerSM * TS_WARPS), hc[33] * 0.064 / (numSMs * tileCtasPerSM * TS_WARPS),
-			        hc[34] * 0.064 / (numSMs * tileCtasPerSM * TS_WARPS), hc[35] * 0.064 / (numSMs * tileCtasPerSM * TS_WARPS));
 		if (dbg && hc[6])
 			fprintf(stderr, "[ssb] k_sieve_search per query: %.1f passes (%.2f redone), %.0f candidate blocks, %.0f probes; gave up on %u\n",
 			        hc[24] / (double)hc[6], hc[27] / (double)hc[6], hc[26] / (double)hc[6], hc[25] / (double)hc[6], hc[28]);

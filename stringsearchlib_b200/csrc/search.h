@@ -32,26 +32,9 @@ struct QDesc {
 	uint8_t listMult[MAX_QGRAMS];
 };
 
-// per-query state of the tile pipeline (tile_path.cuh): written by k_tile_plan between the rounds, read by the tiles of a round
-struct TileQ {
-	unsigned long long tau;          // bound on the k-th best rank key, valid for the pass in flight
-	uint32_t status;                 // 0 = in flight, 1 = complete (k_tile_final writes the result), 2 = handed to k_sieve_search
-	uint32_t gLo;                    // first sieve group not covered by a pass yet
-	uint32_t lastG1, lastLen, lastCreq;   // the pass in flight / just finished: its end, length (groups), required count
-	uint32_t candCount;              // entries in the query's candidate list
-	uint32_t failed;                 // a tile could not finish (a buffer overflowed, bitmap and postings disagree)
-	uint32_t nCand;                  // candidate blocks of the pass in flight (pass-length estimates)
-	uint32_t level0;                 // candCount when the pass in flight was planned
-	uint32_t pad;
-	uint32_t geHist[MAX_QGRAMS + 1]; // candidates appended with exactly c matches
-	uint32_t pad2[3];
-};
-static_assert(sizeof(TileQ) == 192, "TileQ layout");
-
 struct SearchStats {
 	uint32_t nFast = 0, nDense = 0, nWildcard = 0, nEmpty = 0, nOverflow = 0;
 	uint32_t nSieve = 0, nSieveHandover = 0, nSieveGiveUp = 0;   // k_sieve_search: answered / handed to k_fast_search / of those, given up mid-query
-	uint32_t nTile = 0, nTileHandover = 0;                       // tile pipeline: answered / handed to k_sieve_search
 	uint64_t postingsTouched = 0;   // sum over fast queries of posting-list lengths (algorithmic bytes / 4)
 	uint64_t candidates = 0;
 	float msDevice = 0;             // CUDA-event time of the device part of the last batch
@@ -64,12 +47,7 @@ struct SearchWorkspace {
 	DevBuf<uint8_t> qchars, qnorm;
 	DevBuf<uint32_t> qoff;
 	DevBuf<QDesc> desc;
-	DevBuf<uint32_t> fastList, fastList2, fastList3, denseList;   // fastList2: queries k_sieve_search hands to k_fast_search;
-	                                                              // fastList3: queries the tile pipeline hands to k_sieve_search
-	// tile pipeline (tile_path.cuh): per-query state, the tiles of every round, per-query candidate lists
-	DevBuf<TileQ> tileQ;
-	DevBuf<uint4> tiles, tileRecs;
-	DevBuf<unsigned long long> tileCand;
+	DevBuf<uint32_t> fastList, fastList2, denseList;   // fastList2: queries k_sieve_search hands to k_fast_search
 	// [0]=nFast [1]=nDense [2]=work cursor [3]=overflow count [4]=any out-of-band list [5]=handed to k_fast_search
 	// [6]=answered by k_sieve_search [28]=of [5], given up mid-query [12]=k_fast_search cursor; [8..11] = two u64 statistics;
 	// [16..19] k_fast_search and [24..27] k_sieve_search per-pass statistics (SSB_DEBUG)

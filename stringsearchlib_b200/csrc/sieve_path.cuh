@@ -361,15 +361,12 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
                                                              uint32_t* __restrict__ handList, uint32_t limit, uint32_t outStride,
                                                              uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
                                                              float* __restrict__ outScore, unsigned long long* __restrict__ statCounters,
-                                                             uint32_t bufCap, float threshold, uint32_t nIdx, uint32_t curIdx, uint32_t defExt,
-                                                             HostOut ho)
+                                                             uint32_t bufCap, float threshold, uint32_t defExt, HostOut ho)
 {
-	// nIdx / curIdx: which counters hold this launch's list length and work cursor (every fast query, or the ones the tile
-	// pipeline handed over)
 	extern __shared__ __align__(16) unsigned char sv_smem[];
 	SieveShared& sh = *reinterpret_cast<SieveShared*>(sv_smem);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t nFast = counters[nIdx];
+	const uint32_t nFast = counters[0];
 	const uint32_t k = limit;
 	const uint32_t NG = ix.sieveNGroups;
 	const int shift = ix.sieveShift;
@@ -385,7 +382,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 
 	while (true) {
 		__syncthreads();
-		if (tid == 0) sh.query = atomicAdd(&counters[curIdx], 1u);
+		if (tid == 0) sh.query = atomicAdd(&counters[2], 1u);
 		__syncthreads();
 		const uint32_t wi = sh.query;
 		if (wi >= nFast) break;
@@ -456,6 +453,33 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 		bool failed = nSieve > SV_MAXL, tauReal = false;      // (repeated grams: more counted lists than the sieve takes)
 		uint32_t selectAt = min(bufCap / 2, 2 * k + 64);
 		uint32_t level = 0;
+		// Class mode: blocks for the general resolution wait in the slow queue across passes and are resolved once per phase
+		// (or when the queue is half full) instead of after every pass — their postings and bitmap groups have left the caches
+		// by then either way, and each resolution costs the CTA a chain of DRAM round trips. Leaving their terms out for a while
+		// only makes tau looser. Nothing here can be rolled back: an overflow hands the query to k_fast_search.
+		const bool lazySlow = classMode;
+		auto flush_slow = [&](const uint32_t onlyCount) {
+			__syncthreads();
+			const uint32_t n = min(sh.nSlow, (uint32_t)SV_SLOWCAP);
+			// (the count a term needs is the query's own lower bound here, refined per block from tau: the queue holds blocks of
+			// passes with different requirements)
+			if (tid == 0) { sh.defCount = 0; sh.cRej = sh.cmin ? sh.cmin - 1 : 0; }
+			__syncthreads();
+			for (uint32_t i = tid; i < n; i += SV_THREADS) resolve_slow(sh, sh.slowQ[i], onlyCount, sh.tau);
+			__syncthreads();
+			const uint32_t nd = min(sh.defCount, sh.defCap);
+			for (uint32_t i = tid; i < nd; i += SV_THREADS) {
+				const unsigned long long e = sh.defList[i];
+				emit_candidate<U, false>(sh, qn, (uint32_t)e, (uint32_t)(e >> 32));
+			}
+			__syncthreads();
+			if (sh.overflow) failed = true;
+			level = sh.bufCount;
+			__syncthreads();
+			if (tid == 0) { sh.nSlow = 0; sh.defCount = 0; }
+			if (!failed && level > bufCap / 2) { select_smallest<SV_THREADS>(sh, level, k); level = k; }
+		};
+		if (tid == 0) sh.nSlow = 0;
 		for (uint32_t phase = twoPhase ? 0u : 1u; phase < 2 && !failed; ++phase) {
 			__syncthreads();
 			if (phase == 1) {
@@ -520,13 +544,15 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 							if (len > 8 * SV_THREADS) len &= ~(uint32_t)(SV_THREADS - 1);
 						}
 						sh.passG0 = gLo; sh.passG1 = min(NG, gLo + len);
-						sh.nCand = 0; sh.nSlow = 0; sh.defCount = 0;
+						sh.nCand = 0; sh.defCount = 0;
+						if (!sh.classMode) sh.nSlow = 0;
 					}
 				}
 				__syncthreads();
 				SV_TICK(1);
 				if (sh.done) break;
 				const uint32_t w0 = sh.passG0, w1 = sh.passG1, creq = sh.cRej + 1;
+				const uint32_t slowSnap = sh.nSlow;                // (lazy mode) entries of earlier passes
 				if (tid == 0) atomicAdd(&counters[24], 1u);
 				// ---- sieve + resolve, then the blocks left to the general resolution, then what was deferred
 				sieve_dispatch(sh, creq, w0, w1, nSieve, onlyCount);
@@ -536,7 +562,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 				bool redo = false;
 				uint32_t shorter = 0;
 				{
-					{
+					if (!lazySlow) {
 						const uint32_t nSlow = min(sh.nSlow, (uint32_t)SV_SLOWCAP);
 						for (uint32_t i = tid; i < nSlow; i += SV_THREADS) resolve_slow(sh, sh.slowQ[i], onlyCount, sh.tau);
 						if (nSlow) __syncthreads();
@@ -555,7 +581,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 						__syncthreads();
 						if (warp == 0) {
 							sh.geHist[lane + 1] = sh.geSnap[lane + 1];
-							if (lane == 0) { sh.bufCount = level; sh.overflow = 0; }
+							if (lane == 0) { sh.bufCount = level; sh.overflow = 0; if (lazySlow) sh.nSlow = slowSnap; }
 						}
 						redo = true;
 						shorter = (w1 - w0) >> 1;
@@ -581,7 +607,10 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 					selectAt = bufCap / 2;
 				}
 				SV_TICK(4);
+				if (lazySlow && sh.nSlow > (uint32_t)SV_SLOWCAP / 2) { flush_slow(onlyCount); if (failed) break; }
 			}
+			if (lazySlow && !failed) flush_slow(onlyCount);
+			SV_TICK(3);
 		}
 		if (failed) {
 			if (tid == 0) { handList[atomicAdd(&counters[5], 1u)] = q; atomicAdd(&counters[28], 1u); }
