@@ -432,7 +432,7 @@ def main():
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get("k_fast_search_dram_bytes_per_launch")
+                traffic = json.load(f).get(("k_sieve_search" if last_st.get("nSieve", 0) * 2 > args.batch else "k_fast_search") + "_dram_bytes_per_launch")
         except (OSError, ValueError):
             traffic = None
     line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -44,7 +44,10 @@ namespace {
 #define SV_MIN_CTAS 8
 #endif
 constexpr int SV_THREADS = 128;
-constexpr int SV_CCAP = 1024;                           // candidate blocks a pass aims at (its length is chosen accordingly)
+#ifndef SV_CCAP_
+#define SV_CCAP_ 2048
+#endif
+constexpr int SV_CCAP = SV_CCAP_;                           // candidate blocks a pass aims at (its length is chosen accordingly)
 constexpr int SV_WQCAP = 160;                           // per-warp queue of blocks that passed the sieve: < 32 left over + <= 128 pushed
 constexpr int SV_PU = 4;                                // lists of one block resolved at a time (independent load chains)
 constexpr int SV_SLOWCAP = 256;                         // blocks per pass that need the general resolution
