@@ -149,6 +149,10 @@ def main():
                     help="N>1: p2p = export/merge kernels storing into NVLink peer memory with a device-side epoch hand-over, no "
                          "collective at all (default); p2p-barrier = the same stores with two 4-byte all-reduces as barriers and "
                          "the results replicated on every rank; nccl = NCCL all-to-all + all-gather")
+    ap.add_argument("--layout", choices=("shards", "replicas"), default="shards",
+                    help="N > 1: shards = the index split in key ranges, every rank answers the whole batch on its shard, per-query top-k "
+                         "merge across ranks (BASELINE.json's configuration, the default); replicas = every rank holds the whole index "
+                         "and answers 1/N of the batch, no exchange (what a deployment would do with an index that fits one GPU)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -162,6 +166,11 @@ def main():
               "sharding": f"key-range x{world}; per-query top-k merge, exchange={args.exchange}; e2e: every rank returns the merged "
                           f"results of its 1/{world} slice of the batch to its host" if world > 1 else "single shard",
               "l2": "inputs larger than L2: new query batch every step, ~184 KB of postings per query"}
+    replicas = world > 1 and args.layout == "replicas"
+    if replicas:
+        if args.batch % world:
+            raise SystemExit("--layout replicas needs a batch divisible by the number of GPUs")
+        config["sharding"] = f"replicated index x{world}: every rank answers its 1/{world} slice of the batch on the whole index, no exchange"
 
     if args.impl == "reference":
         if rank != 0:
@@ -197,8 +206,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---- index build through the char** entry point (host pointers, like an FFI caller)
-    lo = args.keys * rank // world
-    hi = args.keys * (rank + 1) // world
+    lo = 0 if replicas else args.keys * rank // world
+    hi = args.keys if replicas else args.keys * (rank + 1) // world
     keys = synth.ascii_keys(hi - lo, first=lo)
     ptrs = keys.pointers()
     # first build = cold (CUDA context, memory pool growth, pinned staging allocation); it is reported separately and the
@@ -225,13 +234,14 @@ def main():
         t_build = float(tb.item())
 
     nsteps = args.warmup + args.steps
-    batches = [synth.ascii_queries(args.batch, args.keys, first_query=s * args.batch) for s in range(nsteps)]
+    nb = args.batch // world if replicas else args.batch          # queries this rank answers per step
+    batches = [synth.ascii_queries(nb, args.keys, first_query=s * args.batch + (rank * nb if replicas else 0)) for s in range(nsteps)]
     qptrs = [b.pointers() for b in batches]
     rec_bytes = RECORD_DTYPE.itemsize
-    sliced = world > 1 and args.batch % world == 0
+    sliced = world > 1 and args.batch % world == 0 and not replicas
     use_p2p = sliced and args.exchange in ("p2p", "p2p-barrier")
     use_signal = sliced and args.exchange == "p2p"
-    if world > 1:
+    if world > 1 and not replicas:
         part_q = args.batch // world if sliced else 0
         host_rec = torch.empty((args.batch, args.limit, rec_bytes), dtype=torch.uint8, pin_memory=True)
         host_cnt = torch.empty(args.batch, dtype=torch.int32, pin_memory=True)
@@ -257,7 +267,7 @@ def main():
             ok = torch.zeros(1, device="cuda")
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         use_p2p = bool(ok.item() > 0)
-    if world > 1 and not use_p2p:
+    if world > 1 and not use_p2p and not replicas:
         mine = torch.empty((args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
         merged = torch.empty((args.batch, args.limit, rec_bytes), dtype=torch.uint8, device="cuda")
         mcount = torch.empty(args.batch, dtype=torch.int32, device="cuda")
@@ -360,9 +370,9 @@ def main():
         # (1) end to end through the C ABI with host buffers
         barrier()
         t0 = time.perf_counter()
-        if world == 1:
-            bp = ix.search_batch_raw(qptrs[s], args.batch, args.threshold, args.limit)   # H2D + kernels + D2H inside
-            n_results = int(bp.contents.offsets[args.batch])
+        if world == 1 or replicas:
+            bp = ix.search_batch_raw(qptrs[s], nb, args.threshold, args.limit)   # H2D + kernels + D2H inside
+            n_results = int(bp.contents.offsets[nb])
             ix.free_raw(bp)
         else:
             # sharded: H2D + kernels on every rank, cross-shard merge, then ONE D2H of the merged records
@@ -374,8 +384,8 @@ def main():
         # (2) device part only, the same batch resident in HBM
         barrier()
         t2 = time.perf_counter()
-        ms, msk, st = ix.search_resident(args.batch, args.threshold, args.limit)
-        if world > 1:
+        ms, msk, st = ix.search_resident(nb, args.threshold, args.limit)
+        if world > 1 and not replicas:
             ms += exchange_timed()          # device time of the step = search (engine-stream events) + exchange (default-stream events)
         torch.cuda.synchronize()
         t3 = time.perf_counter()
@@ -387,9 +397,9 @@ def main():
             postings.append(st["postings"])
             last_st = st
             results.append(n_results)
-            assert st["nFast"] == args.batch and st["nDense"] == 0, st
-            h2d = int(batches[s].offsets[-1]) + 4 * (args.batch + 1)
-            d2h = 4 * (args.batch + 1) + 24 * n_results if world == 1 else args.batch * args.limit * rec_bytes + 4 * args.batch
+            assert st["nFast"] == nb and st["nDense"] == 0, st
+            h2d = int(batches[s].offsets[-1]) + 4 * (nb + 1)
+            d2h = 4 * (nb + 1) + 24 * n_results if (world == 1 or replicas) else args.batch * args.limit * rec_bytes + 4 * args.batch
     barrier()
     launches = ssb.kernel_launches() - launches0
     # the timed region of a few steps lasts only milliseconds; keep the identical load running (untimed) until nvidia-smi
@@ -397,7 +407,7 @@ def main():
     t_extra = time.perf_counter()
     extra_steps = 0
     while len(sampler.lines) < 8 and time.perf_counter() - t_extra < 2.0:
-        ix.search_resident(args.batch, args.threshold, args.limit)
+        ix.search_resident(nb, args.threshold, args.limit)
         extra_steps += 1
     clocks = sampler.stop()
     clocks["note"] = f"sampled every 50 ms from the first warm-up step; {extra_steps} extra untimed steps of the same load to reach {len(sampler.lines)} samples"
@@ -424,7 +434,7 @@ def main():
     e2e = args.batch / float(np.mean(e2e_s))
     peak, peak_src = read_peaks()
     nlists_est = 8.0 * 9                                         # 8 B x ~9 gram lookups per query (negligible next to postings)
-    algo_bytes = float(np.mean(postings)) * 4.0 + args.batch * nlists_est + 8.0 * float(np.mean(results))
+    algo_bytes = float(np.mean(postings)) * 4.0 + nb * nlists_est + 8.0 * float(np.mean(results))
     k_ms = float(np.mean(fast_ms))
     achieved = algo_bytes / (k_ms / 1e3) / 1e9
     traffic = None
@@ -432,7 +442,7 @@ def main():
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get(("k_sieve_search" if last_st.get("nSieve", 0) * 2 > args.batch else "k_fast_search") + "_dram_bytes_per_launch")
+                traffic = json.load(f).get(("k_sieve_search" if last_st.get("nSieve", 0) * 2 > nb else "k_fast_search") + "_dram_bytes_per_launch")
         except (OSError, ValueError):
             traffic = None
     line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -446,7 +456,7 @@ def main():
             "queries_by_kernel": {"k_sieve_search": last_st.get("nSieve", 0),
                                   "k_fast_search": last_st.get("nFast", 0) - last_st.get("nSieve", 0),
                                   "dense": last_st.get("nDense", 0)},
-            "roofline": {"bound": "hbm", "kernel": "k_sieve_search" if last_st.get("nSieve", 0) * 2 > args.batch else "k_fast_search",
+            "roofline": {"bound": "hbm", "kernel": "k_sieve_search" if last_st.get("nSieve", 0) * 2 > nb else "k_fast_search",
                          "timed": "k_sieve_search + k_fast_search launches of one batch (CUDA events on the engine's stream)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -92,7 +92,8 @@ def kernel_launches():
 
 
 def set_search_path(path):
-    """1 = k_sieve_search first, 0 = k_fast_search alone, -1 = default (1 unless SSB_MERGE is set); identical results (include/ssb_engine.h)."""
+    """1 = k_sieve_search for every query it can take, 0 = k_fast_search alone, -1 = default (per query by posting volume; 0 when
+    SSB_MERGE is set); identical results (include/ssb_engine.h)."""
     if core_library().ssb_set_search_path(int(path)) != 0:
         raise ValueError("search path must be -1, 0 or 1")
 

@@ -235,7 +235,10 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 		d.cls = cls; d.qlen = qlen; d.nGrams = nGrams; d.nLists = nLists; d.cmin = cmin; d.cprom = cprom; d.total = total; d.qbeg = b;
 		d.flags = (shortActive ? 1u : 0u) | ((shortActive && qlen <= g) ? 2u : 0u) | ((sieveOk && !shortActive && cls == QC_FAST) ? 4u : 0u);
 		outCount[q] = 0;
-		if (cls == QC_FAST) fastList[atomicAdd(&counters[0], 1u)] = q;
+		if (cls == QC_FAST) {
+			fastList[atomicAdd(&counters[0], 1u)] = q;
+			atomicAdd(reinterpret_cast<unsigned long long*>(counters + 30), (unsigned long long)total);      // postings of the batch's fast queries
+		}
 		else if (cls == QC_DENSE || cls == QC_WILDCARD) denseList[atomicAdd(&counters[1], 1u)] = q;
 	}
 }
@@ -640,6 +643,14 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	ws.counters.zero(s);
 	const U* qc = reinterpret_cast<const U*>(ws.qchars.get());
 	U* qn = reinterpret_cast<U*>(ws.qnorm.get());
+	// k_sieve_search pays a fixed price per query (set-up, pass plans, the general resolutions) and then grows slowly with the
+	// lists; the register merge of k_fast_search costs nothing up front and grows with every posting. Measured on B200 (batch
+	// 4096, ~9 lists per query): a tie at ~23 000 postings per query (a 5M-key index), k_sieve_search 10 % ahead at 46 000,
+	// 35 % behind at 6 000. The two kernels run one after the other, so the choice is made per batch, on the device, from the
+	// mean posting volume of its fast queries (k_sieve_search hands the whole batch over when it is below the mark).
+	// ssb_set_search_path(1) sends every eligible query to k_sieve_search (the parity tests cover it on small indexes that way).
+	static const uint32_t sieveMinDefault = getenv("SSB_SIEVE_MIN_POSTINGS") ? (uint32_t)atoll(getenv("SSB_SIEVE_MIN_POSTINGS")) : 28000u;
+	const uint32_t sieveMinTotal = g_search_path.load(std::memory_order_relaxed) == 1 ? 0u : sieveMinDefault;
 	k_query_prep<U><<<grid_for((size_t)nq * 32), 256, 0, s>>>(v, qc, ws.qoff.get(), nq, threshold, limit, qn, ws.desc.get(),
 	                                                          ws.fastList.get(), ws.denseList.get(), ws.counters.get(),
 	                                                          ws.outCount.get());
@@ -667,7 +678,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		const unsigned sgrid = (unsigned)std::min<size_t>((size_t)numSMs * sieveCtasPerSM, std::max<uint32_t>(nq, 1));
 		k_sieve_search<U><<<sgrid, SV_THREADS, svBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(), ws.fastList2.get(),
 		                                                    limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(),
-		                                                    statCounters, bufCap, threshold, defExt, ho);
+		                                                    statCounters, bufCap, threshold, defExt, sieveMinTotal, ho);
 		SSB_LAUNCH_CHECK();
 	}
 	const uint32_t* fl = useSieve ? ws.fastList2.get() : ws.fastList.get();

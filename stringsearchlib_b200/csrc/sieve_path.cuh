@@ -364,12 +364,18 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
                                                              uint32_t* __restrict__ handList, uint32_t limit, uint32_t outStride,
                                                              uint32_t* __restrict__ outCount, uint32_t* __restrict__ outKid,
                                                              float* __restrict__ outScore, unsigned long long* __restrict__ statCounters,
-                                                             uint32_t bufCap, float threshold, uint32_t defExt, HostOut ho)
+                                                             uint32_t bufCap, float threshold, uint32_t defExt, uint32_t minMeanTotal, HostOut ho)
 {
 	extern __shared__ __align__(16) unsigned char sv_smem[];
 	SieveShared& sh = *reinterpret_cast<SieveShared*>(sv_smem);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t nFast = counters[0];
+	// batches of short queries are k_fast_search's (search.cu): the list is handed over as it is (LPT order included)
+	if (*reinterpret_cast<const unsigned long long*>(counters + 30) < (unsigned long long)minMeanTotal * nFast) {
+		for (uint32_t i = blockIdx.x * SV_THREADS + threadIdx.x; i < nFast; i += gridDim.x * SV_THREADS) handList[i] = fastList[i];
+		if (blockIdx.x == 0 && threadIdx.x == 0) counters[5] = nFast;
+		return;
+	}
 	const uint32_t k = limit;
 	const uint32_t NG = ix.sieveNGroups;
 	const int shift = ix.sieveShift;
