@@ -237,7 +237,10 @@ __global__ void __launch_bounds__(256) k_query_prep(IndexView ix, const U* __res
 		outCount[q] = 0;
 		if (cls == QC_FAST) {
 			fastList[atomicAdd(&counters[0], 1u)] = q;
-			atomicAdd(reinterpret_cast<unsigned long long*>(counters + 30), (unsigned long long)total);      // postings of the batch's fast queries
+			// posting volume of the batch's fast queries, the figure the choice of kernel is made from (run_device). A query
+			// that needs two or more matches from the start (a threshold) has no dense first phase in k_sieve_search and
+			// counts five-fold: measured, the sieve is 2x ahead of the merge there from ~18 000 postings per query on
+			atomicAdd(reinterpret_cast<unsigned long long*>(counters + 30), (unsigned long long)total * (cmin >= 2 ? 5u : 1u));
 		}
 		else if (cls == QC_DENSE || cls == QC_WILDCARD) denseList[atomicAdd(&counters[1], 1u)] = q;
 	}
@@ -647,7 +650,8 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	// lists; the register merge of k_fast_search costs nothing up front and grows with every posting. Measured on B200 (batch
 	// 4096, ~9 lists per query): a tie at ~23 000 postings per query (a 5M-key index), k_sieve_search 10 % ahead at 46 000,
 	// 35 % behind at 6 000. The two kernels run one after the other, so the choice is made per batch, on the device, from the
-	// mean posting volume of its fast queries (k_sieve_search hands the whole batch over when it is below the mark).
+	// mean posting volume of its fast queries (k_sieve_search hands the whole batch over when it is below the mark; queries
+	// under a threshold count five-fold, see k_query_prep).
 	// ssb_set_search_path(1) sends every eligible query to k_sieve_search (the parity tests cover it on small indexes that way).
 	static const uint32_t sieveMinDefault = getenv("SSB_SIEVE_MIN_POSTINGS") ? (uint32_t)atoll(getenv("SSB_SIEVE_MIN_POSTINGS")) : 28000u;
 	const uint32_t sieveMinTotal = g_search_path.load(std::memory_order_relaxed) == 1 ? 0u : sieveMinDefault;
@@ -780,6 +784,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		if (dbg && hc[6] && hc[34])
 			fprintf(stderr, "[ssb] k_sieve_search kilocycles per query: set-up %.1f, plan %.1f, sieve+resolve %.1f, slow+deferred %.1f, select %.1f, final %.1f\n",
 			        hc[32] * 0.064 / hc[6], hc[33] * 0.064 / hc[6], hc[34] * 0.064 / hc[6], hc[35] * 0.064 / hc[6], hc[36] * 0.064 / hc[6], hc[37] * 0.064 / hc[6]),
+			fprintf(stderr, "[ssb]   of slow+deferred: thread 0's own general resolutions %.1f, waiting for the CTA's %.1f\n", hc[38] * 0.064 / hc[6], hc[39] * 0.064 / hc[6]),
 			fprintf(stderr, "[ssb]   of sieve+resolve, warp 0: loads + counters %.1f, queue pushes %.1f, resolve rounds %.1f\n", hc[40] * 0.064 / hc[6],
 			        hc[41] * 0.064 / hc[6], hc[42] * 0.064 / hc[6]);
 		st->postingsTouched = postings;

@@ -474,8 +474,11 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 			// passes with different requirements)
 			if (tid == 0) { sh.defCount = 0; sh.cRej = sh.cmin ? sh.cmin - 1 : 0; }
 			__syncthreads();
+			SV_TICK(3);
 			for (uint32_t i = tid; i < n; i += SV_THREADS) resolve_slow(sh, sh.slowQ[i], onlyCount, sh.tau);
+			SV_TICK(6);
 			__syncthreads();
+			SV_TICK(7);
 			const uint32_t nd = min(sh.defCount, sh.defCap);
 			for (uint32_t i = tid; i < nd; i += SV_THREADS) {
 				const unsigned long long e = sh.defList[i];
