@@ -438,6 +438,54 @@ Sorted sort_pairs(DevBuf<uint64_t>& k, DevBuf<uint64_t>& kAlt, DevBuf<uint32_t>&
 	return alt ? Sorted{kAlt.get(), vAlt.get()} : Sorted{k.get(), v.get()};
 }
 
+// The host copy of the key table travels while the device goes on with edges, grams and bitmaps: a second stream copies
+// keyChars into the pinned staging buffer as soon as k_copy_keys has written it, a host thread then spreads it over the
+// pageable table with parallel page faults (a direct D2H into fresh pageable memory runs at ~2 GB/s).
+struct KeyTableCopy {
+	cudaStream_t s2 = nullptr;
+	cudaEvent_t ev = nullptr;
+	std::thread worker;
+	cudaError_t err = cudaSuccess;
+	~KeyTableCopy()
+	{
+		if (worker.joinable()) worker.join();
+		if (g_exiting.load()) return;
+		if (ev) cudaEventDestroy(ev);
+		if (s2) cudaStreamDestroy(s2);
+	}
+	void start(cudaStream_t s, const uint8_t* d_src, uint8_t* dst, size_t bytes, void* pinned, size_t pinnedBytes)
+	{
+		SSB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		SSB_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+		SSB_CUDA(cudaEventRecord(ev, s));
+		SSB_CUDA(cudaStreamWaitEvent(s2, ev, 0));
+		const bool bounce = pinned && pinnedBytes >= bytes && bytes > (1u << 20);
+		SSB_CUDA(cudaMemcpyAsync(bounce ? pinned : dst, d_src, bytes, cudaMemcpyDeviceToHost, s2));
+		int dev = 0;
+		SSB_CUDA(cudaGetDevice(&dev));
+		worker = std::thread([this, dev, bounce, dst, pinned, bytes] {
+			cudaSetDevice(dev);
+			err = cudaStreamSynchronize(s2);
+			if (err != cudaSuccess || !bounce) return;
+			const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+			std::vector<std::thread> th;
+			const size_t chunk = ((bytes + nt - 1) / nt + 4095) & ~size_t(4095);
+			for (unsigned t = 0; t < nt; ++t) {
+				const size_t b = (size_t)t * chunk;
+				if (b >= bytes) break;
+				const size_t e = std::min(bytes, b + chunk);
+				th.emplace_back([=] { memcpy(dst + b, static_cast<const uint8_t*>(pinned) + b, e - b); });
+			}
+			for (auto& t : th) t.join();
+		});
+	}
+	void finish()
+	{
+		if (worker.joinable()) worker.join();
+		cuda_check(err, "key table D2H", __FILE__, __LINE__);
+	}
+};
+
 template <class U>
 void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t rowSize, uint16_t gSize, uint64_t rowBase,
                 const uint8_t validLut[256], cudaStream_t s, BuildStats* st)
@@ -448,6 +496,7 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 	ix.validLut.alloc(256, s);
 	SSB_CUDA(cudaMemcpyAsync(ix.validLut.get(), validLut, 256, cudaMemcpyHostToDevice, s));
 	hk.reset();
+	KeyTableCopy keyCopy;                                       // joins its thread / frees its stream on every way out
 	// hpp:122 — fewer than two words (or no array): nothing is indexed and every query returns 0
 	if (pw.n < 2 || !pw.chars || rowSize == 0 || gSize == 0 || gSize > MAX_GSIZE) { SSB_CUDA(cudaStreamSynchronize(s)); return; }
 	if (pw.n >= 0xFFFFFFF0ull || pw.totalUnits >= 0xFFFFFFF0ull) throw std::runtime_error("index: more than 2^32 words/units per shard");
@@ -455,13 +504,20 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 	const uint32_t R = (n + rowSize - 1) / rowSize;
 
 	// ---- H2D
-	DevBuf<U> chars(std::max<uint64_t>(pw.totalUnits, 1), s);
-	DevBuf<uint64_t> off(n + 1, s);
-	DevBuf<uint8_t> isNull(n, s);
+	DevBuf<U> charsBuf;
+	DevBuf<uint64_t> offBuf;
+	DevBuf<uint8_t> isNullBuf;
 	DevBuf<float> weight;
-	SSB_CUDA(cudaMemcpyAsync(chars.get(), pw.chars, pw.totalUnits * sizeof(U), cudaMemcpyHostToDevice, s));
-	SSB_CUDA(cudaMemcpyAsync(off.get(), pw.off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-	SSB_CUDA(cudaMemcpyAsync(isNull.get(), pw.isNull, n, cudaMemcpyHostToDevice, s));
+	const U* dChars = static_cast<const U*>(pw.d_chars);
+	const uint64_t* dOff = pw.d_off;
+	const uint8_t* dIsNull = pw.d_isNull;
+	if (!dChars || !dOff || !dIsNull) {
+		charsBuf.alloc(std::max<uint64_t>(pw.totalUnits, 1), s); offBuf.alloc(n + 1, s); isNullBuf.alloc(n, s);
+		SSB_CUDA(cudaMemcpyAsync(charsBuf.get(), pw.chars, pw.totalUnits * sizeof(U), cudaMemcpyHostToDevice, s));
+		SSB_CUDA(cudaMemcpyAsync(offBuf.get(), pw.off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+		SSB_CUDA(cudaMemcpyAsync(isNullBuf.get(), pw.isNull, n, cudaMemcpyHostToDevice, s));
+		dChars = charsBuf.get(); dOff = offBuf.get(); dIsNull = isNullBuf.get();
+	}
 	if (pw.weight) {
 		weight.alloc(n, s);
 		SSB_CUDA(cudaMemcpyAsync(weight.get(), pw.weight, n * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -483,7 +539,7 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 	for (int attempt = 0;; ++attempt) {
 		if (attempt > 4) throw std::runtime_error("index: persistent 64-bit hash collisions");
 		props.zero(s);
-		k_word_spans<U><<<grid_for(n), TPB, 0, s>>>(chars.get(), off.get(), isNull.get(), weight.get(), n, rowSize, ix.validLut.get(),
+		k_word_spans<U><<<grid_for(n), TPB, 0, s>>>(dChars, dOff, dIsNull, weight.get(), n, rowSize, ix.validLut.get(),
 		                                             seed, termBeg.get(), wordTermLen.get(), termHash.get(), edgeValid.get(),
 		                                             rowKeyBeg.get(), rowKeyLen.get(), rowKeyHash.get(), rowValid.get());
 		SSB_LAUNCH_CHECK();
@@ -504,7 +560,7 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 			exclusive_scan_u8_u32(flag.get(), grp.get(), nv, nullptr, s);
 			k_set_leaders<<<grid_for(nv), TPB, 0, s>>>(flag.get(), grp.get(), so.vals, nv, leaders.get());
 			SSB_LAUNCH_CHECK();
-			k_verify_keys<U><<<grid_for(nv), TPB, 0, s>>>(chars.get(), flag.get(), grp.get(), so.vals, leaders.get(), nv, rowKeyBeg.get(),
+			k_verify_keys<U><<<grid_for(nv), TPB, 0, s>>>(dChars, flag.get(), grp.get(), so.vals, leaders.get(), nv, rowKeyBeg.get(),
 			                                              rowKeyLen.get(), rowLeader.get(), isLeaderRow.get(), props.get());
 			SSB_LAUNCH_CHECK();
 		}
@@ -542,7 +598,7 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 			exclusive_scan_u8_u32(flag.get(), grp.get(), nEdgeWords, nullptr, s);
 			k_set_leaders<<<grid_for(nEdgeWords), TPB, 0, s>>>(flag.get(), grp.get(), so.vals, nEdgeWords, leaders.get());
 			SSB_LAUNCH_CHECK();
-			k_verify_terms<U><<<grid_for(nEdgeWords), TPB, 0, s>>>(chars.get(), ix.validLut.get(), flag.get(), grp.get(), so.vals,
+			k_verify_terms<U><<<grid_for(nEdgeWords), TPB, 0, s>>>(dChars, ix.validLut.get(), flag.get(), grp.get(), so.vals,
 			                                                       leaders.get(), nEdgeWords, termBeg.get(), wordTermLen.get(),
 			                                                       wordLeader.get(), isLeaderWord.get(), props.get());
 			SSB_LAUNCH_CHECK();
@@ -646,12 +702,18 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 	ix.keyChars.alloc((size_t)keyUnits * sizeof(U), s);
 	ix.keyRow.alloc(K, s);
 	ix.keyHash.alloc(K, s);
-	k_copy_terms<U><<<grid_for(T), TPB, 0, s>>>(chars.get(), ix.validLut.get(), termWord.get(), termBeg.get(), ix.termOff.get(), T,
+	k_copy_terms<U><<<grid_for(T), TPB, 0, s>>>(dChars, ix.validLut.get(), termWord.get(), termBeg.get(), ix.termOff.get(), T,
 	                                            reinterpret_cast<U*>(ix.termChars.get()));
 	SSB_LAUNCH_CHECK();
-	k_copy_keys<U><<<grid_for(K), TPB, 0, s>>>(chars.get(), kidRowLocal.get(), rowKeyBeg.get(), ix.keyOff.get(), K, rowBase,
+	k_copy_keys<U><<<grid_for(K), TPB, 0, s>>>(dChars, kidRowLocal.get(), rowKeyBeg.get(), ix.keyOff.get(), K, rowBase,
 	                                           reinterpret_cast<U*>(ix.keyChars.get()), ix.keyRow.get(), ix.keyHash.get());
 	SSB_LAUNCH_CHECK();
+	// host key table: on its way from here on (the staging buffer is free: the upload of the words was ordered before k_copy_keys)
+	hk.K = K;
+	hk.charBytes = (size_t)keyUnits * sizeof(U);
+	hk.chars = static_cast<uint8_t*>(malloc(hk.charBytes ? hk.charBytes : 1));
+	if (!hk.chars) throw std::runtime_error("index: out of host memory for the key table");
+	if (hk.charBytes) keyCopy.start(s, ix.keyChars.get(), hk.chars, hk.charBytes, pw.pinnedScratch, pw.pinnedScratchBytes);
 	// short terms list (hpp:82-85)
 	{
 		DevBuf<uint32_t> pos(T, s);
@@ -769,27 +831,7 @@ void build_impl(DeviceIndex& ix, HostKeys& hk, const PackedWords& pw, uint16_t r
 	ix.multiEdgeKeys = hp.multiEdge != 0;
 	ix.wmax = ordered_to_float(hp.wmaxOrdered);
 	ix.maxTermLen = hp.maxTermLen; ix.maxKeyLen = hp.maxKeyLen;
-	hk.K = K;
-	hk.charBytes = (size_t)keyUnits * sizeof(U);
-	hk.chars = static_cast<uint8_t*>(malloc(hk.charBytes ? hk.charBytes : 1));
-	if (!hk.chars) throw std::runtime_error("index: out of host memory for the key table");
-	const bool bounce = pw.pinnedScratch && pw.pinnedScratchBytes >= hk.charBytes && hk.charBytes > (1u << 20);
-	// D2H into pinned scratch at PCIe speed, then a multi-threaded copy into the pageable table (parallel page faults);
-	// a direct D2H into fresh pageable memory runs at ~2 GB/s
-	SSB_CUDA(cudaMemcpyAsync(bounce ? pw.pinnedScratch : hk.chars, ix.keyChars.get(), hk.charBytes, cudaMemcpyDeviceToHost, s));
-	SSB_CUDA(cudaStreamSynchronize(s));
-	if (bounce) {
-		const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
-		std::vector<std::thread> th;
-		const size_t chunk = ((hk.charBytes + nt - 1) / nt + 4095) & ~size_t(4095);
-		for (unsigned t = 0; t < nt; ++t) {
-			const size_t b = (size_t)t * chunk;
-			if (b >= hk.charBytes) break;
-			const size_t e = std::min(hk.charBytes, b + chunk);
-			th.emplace_back([&, b, e] { memcpy(hk.chars + b, static_cast<const uint8_t*>(pw.pinnedScratch) + b, e - b); });
-		}
-		for (auto& t : th) t.join();
-	}
+	keyCopy.finish();                                           // (usually there already: it started before the grams)
 	if (st) { st->msD2H = tPhase.lap(); st->msTotal = tAll.lap(); }
 }
 

@@ -184,6 +184,8 @@ ssb_index* create_from_pointers(const C* const* words, uint64_t size, uint16_t r
 	SSB_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
 	auto t0 = std::chrono::steady_clock::now();
 	PackedWords pw;
+	DevBuf<uint8_t> dChars, dNull;                      // the words on the device (uploaded while they are packed); freed in stream order
+	DevBuf<uint64_t> dOff;
 	std::lock_guard<std::mutex> stagingLock(g_staging.mu);
 	auto& off = g_staging.off;
 	auto& isNull = g_staging.isNull;
@@ -212,17 +214,41 @@ ssb_index* create_from_pointers(const C* const* words, uint64_t size, uint16_t r
 		const uint64_t total = chunkSum[nt];
 		charsBytes.reserve((std::max<uint64_t>(total, 1) + size) * sizeof(C));   // + terminators: doubles as the key-table bounce buffer
 		C* c = reinterpret_cast<C*>(charsBytes.get());
-		// pass 2: globalise the offsets and gather the code units into one pinned CSR buffer
-		parallel_for(size, nt, [&](unsigned t, uint64_t b, uint64_t e) {
+		// pass 2: globalise the offsets and gather the code units into one pinned CSR buffer. Every packer thread uploads its
+		// part in a few pieces as it goes (all on the build's stream, in any order: the build's first kernel comes after all of
+		// them), so the H2D copy of the words hides behind the packing instead of following it
+		dChars.alloc(std::max<uint64_t>(total, 1) * sizeof(C), ix->stream);
+		dOff.alloc(size + 1, ix->stream);
+		dNull.alloc(size, ix->stream);
+		SSB_CUDA(cudaMemcpyAsync(dNull.get(), nu, size, cudaMemcpyHostToDevice, ix->stream));
+		SSB_CUDA(cudaMemcpyAsync(dOff.get(), o, sizeof(uint64_t), cudaMemcpyHostToDevice, ix->stream));      // o[0] = 0
+		int dev = 0;
+		SSB_CUDA(cudaGetDevice(&dev));
+		std::vector<cudaError_t> upErr(nt, cudaSuccess);
+		cudaStream_t up = ix->stream;
+		uint8_t* dC = dChars.get();
+		uint64_t* dO = dOff.get();
+		parallel_for(size, nt, [&, dev, up, dC, dO](unsigned t, uint64_t b, uint64_t e) {
+			cudaSetDevice(dev);
 			const uint64_t base = chunkSum[t];
 			uint64_t prev = base;      // == global o[b]
-			for (uint64_t i = b; i < e; ++i) {
-				const uint64_t end = o[i + 1] + base;
-				if (words[i]) memcpy(c + prev, words[i], (end - prev) * sizeof(C));
-				o[i + 1] = end;
-				prev = end;
+			const uint64_t piece = std::max<uint64_t>((e - b + 3) / 4, 1);
+			for (uint64_t pb = b; pb < e; pb += piece) {
+				const uint64_t pe = std::min(e, pb + piece), first = prev;
+				for (uint64_t i = pb; i < pe; ++i) {
+					const uint64_t end = o[i + 1] + base;
+					if (words[i]) memcpy(c + prev, words[i], (end - prev) * sizeof(C));
+					o[i + 1] = end;
+					prev = end;
+				}
+				cudaError_t er = cudaSuccess;
+				if (prev > first) er = cudaMemcpyAsync(dC + first * sizeof(C), c + first, (prev - first) * sizeof(C), cudaMemcpyHostToDevice, up);
+				if (er == cudaSuccess) er = cudaMemcpyAsync(dO + pb + 1, o + pb + 1, (pe - pb) * sizeof(uint64_t), cudaMemcpyHostToDevice, up);
+				if (er != cudaSuccess) upErr[t] = er;
 			}
 		});
+		for (cudaError_t er : upErr) SSB_CUDA(er);
+		pw.d_chars = dChars.get(); pw.d_off = dOff.get(); pw.d_isNull = dNull.get();
 		if (weight) {
 			wts.reserve(size);
 			memcpy(wts.get(), weight, size * sizeof(float));

@@ -110,6 +110,11 @@ struct PackedWords {
 	const float* weight = nullptr;  // [n] or nullptr
 	uint64_t n = 0;
 	uint64_t totalUnits = 0;
+	// optional: the same three arrays already on the device (uploads enqueued on the build's stream by the packer, chunk by chunk
+	// while it was still packing); the build then allocates and copies nothing
+	const void* d_chars = nullptr;
+	const uint64_t* d_off = nullptr;
+	const uint8_t* d_isNull = nullptr;
 	// optional pinned scratch the build may overwrite once the input has been uploaded (bounce buffer of the key-table D2H)
 	void* pinnedScratch = nullptr;
 	size_t pinnedScratchBytes = 0;

@@ -43,7 +43,10 @@ namespace {
 #ifndef SV_MIN_CTAS
 #define SV_MIN_CTAS 8
 #endif
-constexpr int SV_THREADS = 128;
+#ifndef SV_THREADS_
+#define SV_THREADS_ 128
+#endif
+constexpr int SV_THREADS = SV_THREADS_;
 #ifndef SV_CCAP_
 #define SV_CCAP_ 2048
 #endif
