@@ -355,7 +355,7 @@ def main():
             host_cnt.copy_(mcount, non_blocking=True)
             torch.cuda.synchronize()
 
-    dev_ms, fast_ms, e2e_s, step_s, postings, results = [], [], [], [], [], []
+    dev_ms, fast_ms, e2e_s, step_s, postings, results, exch_ms = [], [], [], [], [], [], []
     last_st = {}
     sampler = ClockSampler(local_rank)
     launches0 = 0
@@ -386,7 +386,10 @@ def main():
         t2 = time.perf_counter()
         ms, msk, st = ix.search_resident(nb, args.threshold, args.limit)
         if world > 1 and not replicas:
-            ms += exchange_timed()          # device time of the step = search (engine-stream events) + exchange (default-stream events)
+            xms = exchange_timed()
+            ms += xms
+            if timed:
+                exch_ms.append(xms)          # device time of the step = search (engine-stream events) + exchange (default-stream events)
         torch.cuda.synchronize()
         t3 = time.perf_counter()
         if timed:
@@ -420,6 +423,7 @@ def main():
         return t.tolist()
 
     step_s, e2e_s, dev_ms, fast_ms = agg_max(step_s), agg_max(e2e_s), agg_max(dev_ms), agg_max(fast_ms)
+    exch_ms = agg_max(exch_ms) if exch_ms else []
     if xprof and rank == 0:
         m = np.median(np.array(xprof), axis=0)
         sys.stderr.write(f"[exchange ms] export={m[0]:.3f} barrier1={m[1]:.3f} merge={m[2]:.3f} barrier2={m[3]:.3f}\n")
@@ -466,6 +470,8 @@ def main():
                             "device_only_keys_per_s": (hi - lo) / max((bms["total"] - bms["pack"]) / 1e3, 1e-9),
                             "terms": info["T"], "grams": info["G"], "postings": info["P"], "device_bytes": info["deviceBytes"]},
             "host_cores": cores}
+    if exch_ms:
+        line["exchange_ms_per_step"] = float(np.mean(exch_ms))      # device time of export + cross-shard merge (max over ranks), part of ms_per_step
     if world == 1 and not args.no_cpu_baseline:
         try:
             cb = reference_leg(args, args.cpu_keys, min(args.cpu_queries, args.batch), cores, steps=1, warmup=0)

@@ -7,9 +7,13 @@ from stringsearchlib_b200 import synth, api
 keys = synth.ascii_keys(30000)
 q = synth.queries_from(keys, 256)
 with ssb.Index(keys, 1) as ix:
-    r = ix.search_batch(q, 0.0, 100)
-    r = ix.search_batch(q, 0.3, 1000)
-    print("identity", ix.info()["identity"], len(r.kids))
+    for path in (1, 0, -1):                      # k_sieve_search for every query it takes, k_fast_search alone, the default choice
+        ssb.set_search_path(path)
+        r = ix.search_batch(q, 0.0, 100)
+        r = ix.search_batch(q, 0.3, 1000)
+        r = ix.search_batch(q, 0.0, 2000)
+        print("identity", ix.info()["identity"], path, len(r.kids))
+ssb.set_search_path(1)
 words, w = synth.key_desc_rows(8000)
 with ssb.Index(words, 2, w) as ix:
     r = ix.search_batch(synth.queries_from(words, 128, stride=2), 0.0, 50)

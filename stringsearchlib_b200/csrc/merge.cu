@@ -61,8 +61,7 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
 __global__ void k_export_records_p2p(const uint32_t* __restrict__ outCount, const uint32_t* __restrict__ outKid,
                                      const float* __restrict__ outScore, uint32_t stride, uint32_t nq, uint32_t limit,
                                      const uint32_t* __restrict__ keyOff, const uint64_t* __restrict__ keyRow,
-                                     const uint64_t* __restrict__ keyHash, PeerPtrs peers, uint32_t nRanks, uint32_t myRank,
-                                     uint32_t* __restrict__ done, PeerFlags flags, uint32_t epoch)
+                                     const uint64_t* __restrict__ keyHash, PeerPtrs peers, uint32_t nRanks, uint32_t myRank)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < (uint64_t)nq * limit) {
@@ -70,21 +69,15 @@ __global__ void k_export_records_p2p(const uint32_t* __restrict__ outCount, cons
 		const uint32_t part = nq / nRanks, j = q / part, ql = q - j * part;
 		peers.p[j][((size_t)myRank * part + ql) * limit + r] = make_record(q, r, outCount, outKid, outScore, stride, keyOff, keyRow, keyHash);
 	}
-	if (!done) return;
-	// device-side signal instead of a collective: the last CTA to finish tells every peer "epoch delivered". The fence of
-	// thread 0 is cumulative over the CTA's stores (ordered before it by the barrier); the release stores publish them.
-	__shared__ uint32_t sLast;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence_system();
-		sLast = atomicAdd(done, 1u) == gridDim.x - 1;
-	}
-	__syncthreads();
-	if (sLast) {
-		if (threadIdx.x == 0) *done = 0;
-		__threadfence_system();
-		if (threadIdx.x < nRanks) st_release_sys(flags.p[threadIdx.x] + myRank, epoch);
-	}
+}
+
+// device-side signal instead of a collective, launched behind the export kernel on the same stream: the records of this rank
+// are complete at the kernel boundary; one system-scope fence (cumulative over them) and one release store per peer publish
+// "epoch delivered". (Round 1 had the last CTA of the export kernel do this after a system fence in EVERY CTA.)
+__global__ void k_signal_epoch(PeerFlags flags, uint32_t nRanks, uint32_t myRank, uint32_t epoch)
+{
+	__threadfence_system();
+	if (threadIdx.x < nRanks) st_release_sys(flags.p[threadIdx.x] + myRank, epoch);
 }
 
 __device__ __forceinline__ bool rec_less(uint64_t a1, uint64_t b1, uint64_t a2, uint64_t b2) { return a1 != a2 ? a1 < a2 : b1 < b2; }
@@ -253,17 +246,15 @@ void export_records_p2p(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq,
 	PeerPtrs pp{};
 	for (uint32_t i = 0; i < nRanks; ++i) pp.p[i] = peerRecv[i];
 	const uint64_t n = (uint64_t)nq * limit;
-	PeerFlags pf{};
-	uint32_t* done = nullptr;
-	if (peerFlags) {
-		for (uint32_t i = 0; i < nRanks; ++i) pf.p[i] = peerFlags[i];
-		if (!ws.exportDone.get()) { ws.exportDone.alloc(1, s); ws.exportDone.zero(s); }
-		done = ws.exportDone.get();
-	}
 	k_export_records_p2p<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.outCount.get(), ws.outKid.get(), ws.outScore.get(), limit, nq, limit,
-	                                                                 ix.keyOff.get(), ix.keyRow.get(), ix.keyHash.get(), pp, nRanks, myRank,
-	                                                                 done, pf, epoch);
+	                                                                 ix.keyOff.get(), ix.keyRow.get(), ix.keyHash.get(), pp, nRanks, myRank);
 	SSB_LAUNCH_CHECK();
+	if (peerFlags) {
+		PeerFlags pf{};
+		for (uint32_t i = 0; i < nRanks; ++i) pf.p[i] = peerFlags[i];
+		k_signal_epoch<<<1, 32, 0, s>>>(pf, nRanks, myRank, epoch);
+		SSB_LAUNCH_CHECK();
+	}
 }
 
 // merges nShards runs per query; when nShards * pow2(limit) exceeds one CTA's shared memory the shards are merged in

@@ -63,7 +63,6 @@ struct SearchWorkspace {
 	DevBuf<uint64_t> csrRow, csrStr;
 	// dense scratch
 	DevBuf<uint32_t> cnt, entry;
-	DevBuf<uint32_t> exportDone;            // CTA counter of the signalling export kernel
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
 	uint32_t capQ = 0, stride = 0;
 	size_t capChars = 0;
