@@ -508,6 +508,46 @@ def test_properties_full_size(ssb):
             assert exact.query(i)[3][0] == keys.get(1000 + i)
 
 
+def test_c4_full_size_both_kernels_agree(ssb):
+    """BASELINE.json's headline configuration at full size (10M keys, batch 4096, top-100; the oracle is not run): the
+    default choice there is k_sieve_search, and the register merge of k_fast_search — a different algorithm over the same
+    postings — must give bit-identical lists; plus the size-independent properties."""
+    from stringsearchlib_b200 import synth
+    n, nq = 10_000_000, 4096
+    keys = synth.ascii_keys(n)
+    with ssb.Index(keys, 1) as ix:
+        info = ix.info()
+        assert info["identity"] and info["uniformW"] and info["G"] == 26 ** 3
+        q = synth.ascii_queries(nq, n)
+        r1 = ix.search_batch(q, 0.0, 100)
+        _, _, st = ix.search_resident(nq, 0.0, 100)
+        assert st["nFast"] == nq and st["nDense"] == 0 and st["nSieve"] + st["nSieveHandover"] == nq and st["nSieve"] > nq // 2, st
+        assert np.all(np.diff(r1.offsets) == 100)
+        sc = r1.scores.reshape(nq, 100)
+        kid = r1.kids.reshape(nq, 100)
+        assert np.all(sc[:, :-1] >= sc[:, 1:])
+        same = sc[:, :-1] == sc[:, 1:]
+        assert np.all(kid[:, :-1][same] < kid[:, 1:][same])          # ties: kid ascending
+        try:
+            ssb.set_search_path(0)
+            r0 = ix.search_batch(q, 0.0, 100)
+            _, _, st0 = ix.search_resident(nq, 0.0, 100)
+        finally:
+            ssb.set_search_path(-1)
+        assert st0["nSieve"] == 0 and st0["nFast"] == nq, st0
+        assert np.array_equal(r1.offsets, r0.offsets) and np.array_equal(r1.kids, r0.kids)
+        assert np.array_equal(r1.scores.view(np.uint32), r0.scores.view(np.uint32))
+        # under a threshold (C5-like: 0.5, top-1000) the two kernels must agree as well
+        ra = ix.search_batch(q.slice(0, 512), 0.5, 1000)
+        try:
+            ssb.set_search_path(0)
+            rb = ix.search_batch(q.slice(0, 512), 0.5, 1000)
+        finally:
+            ssb.set_search_path(-1)
+        assert np.array_equal(ra.offsets, rb.offsets) and np.array_equal(ra.kids, rb.kids)
+        assert np.array_equal(ra.scores.view(np.uint32), rb.scores.view(np.uint32))
+
+
 def test_index_save_load_round_trip(ssb, oracle_built, tmp_path):
     """a saved and re-loaded index has bit-identical tables and answers bit-identically (narrow with
     descriptions + weights + short terms, and wide gSize=2)."""
