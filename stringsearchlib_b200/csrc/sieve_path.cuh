@@ -47,6 +47,9 @@ namespace {
 #define SV_THREADS_ 128
 #endif
 constexpr int SV_THREADS = SV_THREADS_;
+#ifndef SV_DYNAMIC
+#define SV_DYNAMIC 1
+#endif
 #ifndef SV_CCAP_
 #define SV_CCAP_ 2048
 #endif
@@ -79,6 +82,7 @@ struct SieveShared {
 	uint32_t promotedKey;
 	uint32_t bufCount, overflow, query, selPrefixLo, selK;
 	uint32_t nCand, nProbe, nSlow;
+	uint32_t dyn, nGe2, kWant, maxPos, switchGrp;       // dynamic pass (sieve_groups<2, true>): see there
 	uint32_t tim[4];                                    // SV_TIMING: warp 0's cycles >> 6 in the sieve loads, the queue pushes, the resolve rounds
 	uint32_t passG0, passG1, cRej, done;
 	uint32_t qlen, nGrams, cmin, cprom, nLists, sumMult;
@@ -97,6 +101,14 @@ __device__ __noinline__ void sieve_emit(SieveShared& sh, uint32_t term, uint32_t
 		if (key < tau) {
 			append_key(sh, key);
 			atomicAdd(&sh.geHist[c], 1u);
+			if (sh.dyn && atomicAdd(&sh.nGe2, 1u) + 1 == sh.kWant) {
+				// the k-th candidate with two or more matches of a dynamic pass: all k lie below the end of the furthest chunk
+				// any warp has started, so from there on a term needs three matches (chunks further down switch to c = 3)
+				const uint32_t x = *reinterpret_cast<volatile uint32_t*>(&sh.maxPos);
+				const unsigned long long xid = min(((unsigned long long)x * SIEVE_GROUP_BLOCKS) << sh.ix.sieveShift, 0xFFFFFFFFull);
+				atomicMin(&sh.tau, (((unsigned long long)sh.exactKey[2]) << 32) | xid);
+				*reinterpret_cast<volatile uint32_t*>(&sh.switchGrp) = x;
+			}
 		}
 	} else {
 		const uint32_t di = atomicAdd(&sh.defCount, 1u);
@@ -252,11 +264,40 @@ __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t b
 // (hpp:289-298 counts once per window), so the threshold counter needs no multiplicities. Every warp streams 32 consecutive
 // groups per step, collects the blocks that pass in a queue of its own and resolves them 32 at a time — while the groups it
 // needs again are still in L1, without a CTA-wide barrier, and while the other warps keep streaming.
+// one bitmap step of a warp: lane l streams groups gA and gB of every counted list through the bit-sliced threshold counter;
+// m = the blocks that at least CREQ lists hit (3 words of group A, 3 of group B)
 template <int CREQ>
+__device__ __forceinline__ void sieve_step(const SieveShared& sh, const uint32_t nS, const uint32_t gA, const uint32_t gB, const uint32_t g1, uint32_t (&m)[6])
+{
+	uint32_t ga[CREQ], gb[CREQ], gc[CREQ], ha[CREQ], hb[CREQ], hc[CREQ];
+#pragma unroll
+	for (int c = 0; c < CREQ; ++c) { ga[c] = 0; gb[c] = 0; gc[c] = 0; ha[c] = 0; hb[c] = 0; hc[c] = 0; }
+	const bool onA = gA < g1, onB = gB < g1;
+#pragma unroll 4
+	for (uint32_t j = 0; j < nS; ++j) {
+		const uint4* ptr = sh.sievePtr[j];
+		const uint4 x = onA ? __ldg(ptr + gA) : make_uint4(0, 0, 0, 0);      // { first posting, 3 x 32 block bits }
+		const uint4 y = onB ? __ldg(ptr + gB) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+		for (int c = CREQ - 1; c >= 1; --c) {
+			ga[c] |= ga[c - 1] & x.y; gb[c] |= gb[c - 1] & x.z; gc[c] |= gc[c - 1] & x.w;
+			ha[c] |= ha[c - 1] & y.y; hb[c] |= hb[c - 1] & y.z; hc[c] |= hc[c - 1] & y.w;
+		}
+		ga[0] |= x.y; gb[0] |= x.z; gc[0] |= x.w; ha[0] |= y.y; hb[0] |= y.z; hc[0] |= y.w;
+	}
+	m[0] = ga[CREQ - 1]; m[1] = gb[CREQ - 1]; m[2] = gc[CREQ - 1]; m[3] = ha[CREQ - 1]; m[4] = hb[CREQ - 1]; m[5] = hc[CREQ - 1];
+}
+
+// DYN (CREQ == 2, the first phase of a query without threshold): the pass runs to the end of the id range and switches from
+// "two lists" to "three lists" on its own. Every warp publishes the end of the chunk it starts (maxPos); the candidate that
+// brings the number of terms with two or more matches to k (sieve_emit) turns maxPos into the bound — k such terms lie below
+// it — and every chunk that starts at or behind it is sieved for three. One pass, and the two-list stretch is exactly as long
+// as the data needs (a planned pass is either too long: candidate blocks for nothing, or too short: another pass).
+template <int CREQ, bool DYN>
 __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, const uint32_t g1, const uint32_t nS, const uint32_t onlyCount)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const unsigned long long tau = sh.tau;
+	unsigned long long tau = sh.tau;
 	uint32_t* wq = sh.wq[warp];
 	uint32_t qn = 0, nc = 0, np = 0;                             // queue fill (warp-uniform); statistics
 	// a warp streams 64 consecutive groups per step, two per lane (all 2 * nS loads of a lane are independent)
@@ -269,25 +310,12 @@ __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, co
 #define SV_TICKW(slot) do { } while (0)
 #endif
 		uint32_t m[6];                                            // blocks that pass: 3 words of group A, 3 of group B
-		{
-			uint32_t ga[CREQ], gb[CREQ], gc[CREQ], ha[CREQ], hb[CREQ], hc[CREQ];
-#pragma unroll
-			for (int c = 0; c < CREQ; ++c) { ga[c] = 0; gb[c] = 0; gc[c] = 0; ha[c] = 0; hb[c] = 0; hc[c] = 0; }
-			const bool onA = gA < g1, onB = gB < g1;
-#pragma unroll 4
-			for (uint32_t j = 0; j < nS; ++j) {
-				const uint4* ptr = sh.sievePtr[j];
-				const uint4 x = onA ? __ldg(ptr + gA) : make_uint4(0, 0, 0, 0);      // { first posting, 3 x 32 block bits }
-				const uint4 y = onB ? __ldg(ptr + gB) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-				for (int c = CREQ - 1; c >= 1; --c) {
-					ga[c] |= ga[c - 1] & x.y; gb[c] |= gb[c - 1] & x.z; gc[c] |= gc[c - 1] & x.w;
-					ha[c] |= ha[c - 1] & y.y; hb[c] |= hb[c - 1] & y.z; hc[c] |= hc[c - 1] & y.w;
-				}
-				ga[0] |= x.y; gb[0] |= x.z; gc[0] |= x.w; ha[0] |= y.y; hb[0] |= y.z; hc[0] |= y.w;
-			}
-			m[0] = ga[CREQ - 1]; m[1] = gb[CREQ - 1]; m[2] = gc[CREQ - 1]; m[3] = ha[CREQ - 1]; m[4] = hb[CREQ - 1]; m[5] = hc[CREQ - 1];
-		}
+		if (DYN) {
+			if (lane == 0) atomicMax(&sh.maxPos, min(base + 64, g1));
+			__syncwarp();
+			if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp)) sieve_step<3>(sh, nS, gA, gB, g1, m);
+			else sieve_step<2>(sh, nS, gA, gB, g1, m);
+		} else sieve_step<CREQ>(sh, nS, gA, gB, g1, m);
 		uint32_t left = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]) + __popc(m[5]);
 		SV_TICKW(0);
 		// rounds: every lane pushes up to `quota` of its blocks, then the queue is drained down to less than a warp's worth.
@@ -323,6 +351,7 @@ __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, co
 				qn -= 32;
 				const uint32_t blk = wq[qn + lane];
 				__syncwarp();
+				if (DYN) tau = *reinterpret_cast<volatile unsigned long long*>(&sh.tau);      // (it tightens while the pass runs)
 				np += resolve_block(sh, blk, onlyCount, tau);
 			}
 			SV_TICKW(2);
@@ -330,6 +359,7 @@ __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, co
 	}
 	if (qn) {
 		const uint32_t blk = (uint32_t)lane < qn ? wq[lane] : INF;
+		if (DYN) tau = *reinterpret_cast<volatile unsigned long long*>(&sh.tau);
 		if (blk != INF) np += resolve_block(sh, blk, onlyCount, tau);
 	}
 #pragma unroll
@@ -340,12 +370,13 @@ __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, co
 __device__ __forceinline__ void sieve_dispatch(SieveShared& sh, uint32_t creq, uint32_t g0, uint32_t g1, uint32_t nS, uint32_t onlyCount)
 {
 	// thresholds without an instantiation of their own use the next lower one: a superset of the blocks, RESOLVE counts exactly
-	if (creq <= 1) sieve_groups<1>(sh, g0, g1, nS, onlyCount);
-	else if (creq == 2) sieve_groups<2>(sh, g0, g1, nS, onlyCount);
-	else if (creq == 3) sieve_groups<3>(sh, g0, g1, nS, onlyCount);
-	else if (creq < 6) sieve_groups<4>(sh, g0, g1, nS, onlyCount);
-	else if (creq < 8) sieve_groups<6>(sh, g0, g1, nS, onlyCount);
-	else sieve_groups<8>(sh, g0, g1, nS, onlyCount);
+	if (sh.dyn) sieve_groups<2, true>(sh, g0, g1, nS, onlyCount);
+	else if (creq <= 1) sieve_groups<1, false>(sh, g0, g1, nS, onlyCount);
+	else if (creq == 2) sieve_groups<2, false>(sh, g0, g1, nS, onlyCount);
+	else if (creq == 3) sieve_groups<3, false>(sh, g0, g1, nS, onlyCount);
+	else if (creq < 6) sieve_groups<4, false>(sh, g0, g1, nS, onlyCount);
+	else if (creq < 8) sieve_groups<6, false>(sh, g0, g1, nS, onlyCount);
+	else sieve_groups<8, false>(sh, g0, g1, nS, onlyCount);
 }
 
 // expected candidate blocks per bitmap word when a block needs >= c of K lists, every list setting a block with probability p
@@ -400,6 +431,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 		if (wi >= nFast) break;
 #if SV_TIMING
 		long long tick = clock64();
+		const long long tQuery = tick;
 #endif
 		const uint32_t q = fastList[wi];
 		const QDesc& d = desc[q];
@@ -512,6 +544,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 			const uint32_t onlyCount = (twoPhase && phase == 1) ? 1u : 0u;
 			uint32_t gLo = 0, lastG1 = 0;
 			uint32_t lastCreq = 0, lastLen = 0, lastCands = 0, forceLen = 0;
+			bool hadRedo = false;
 			SV_TICK(0);
 			while (gLo < NG) {
 				__syncthreads();                      // the previous pass is complete (its counters and plan have been read)
@@ -557,6 +590,16 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 							const float l = 0.7f * (float)want / rate;
 							len = l >= (float)NG ? NG : max(1u, (uint32_t)l);
 							if (len > 8 * SV_THREADS) len &= ~(uint32_t)(SV_THREADS - 1);
+						}
+						// the first phase of a query without threshold runs as ONE dynamic pass to the end of the range (sieve_groups<2, true>)
+						// unless a pass had to be redone (then planned passes, which can be rolled back, take over)
+						const bool dyn = SV_DYNAMIC && twoPhase && phase == 0 && creq == 2 && !forceLen && !hadRedo;
+						sh.dyn = dyn;
+						if (dyn) {
+							len = NG - gLo;
+							uint32_t ge2 = 0;
+							for (uint32_t c2 = 2; c2 <= nGrams; ++c2) ge2 += sh.geHist[c2];
+							sh.nGe2 = ge2; sh.kWant = k; sh.maxPos = gLo; sh.switchGrp = ge2 >= k ? gLo : 0xFFFFFFFFu;
 						}
 						sh.passG0 = gLo; sh.passG1 = min(NG, gLo + len);
 						sh.nCand = 0; sh.defCount = 0;
@@ -605,6 +648,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 				if (redo) {
 					if (w1 - w0 <= 1) { failed = true; break; }
 					forceLen = max(1u, shorter);
+					hadRedo = true;
 					if (tid == 0) atomicAdd(&counters[27], 1u);
 					continue;
 				}
@@ -658,7 +702,15 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 		}
 		SV_TICK(5);
 #if SV_TIMING
-		if (tid == 0) { atomicAdd(&counters[40], sh.tim[0]); atomicAdd(&counters[41], sh.tim[1]); atomicAdd(&counters[42], sh.tim[2]); }
+		if (tid == 0) {
+			atomicAdd(&counters[40], sh.tim[0]); atomicAdd(&counters[41], sh.tim[1]); atomicAdd(&counters[42], sh.tim[2]);
+			// the slowest query of the batch, the number of queries over 1 and 2 megacycles, and when the last query started / ended
+			const uint32_t kc = (uint32_t)((clock64() - tQuery) >> 10);
+			atomicMax(&counters[43], kc);
+			if (kc > 1000) atomicAdd(&counters[44], 1u);
+			if (kc > 2000) atomicAdd(&counters[45], 1u);
+			if (kc > 500) atomicAdd(&counters[46], 1u);
+		}
 #endif
 	}
 }
