@@ -56,7 +56,7 @@ constexpr int SV_THREADS = SV_THREADS_;
 constexpr int SV_CCAP = SV_CCAP_;                           // candidate blocks a pass aims at (its length is chosen accordingly)
 constexpr int SV_WQCAP = 160;                           // per-warp queue of blocks that passed the sieve: < 32 left over + <= 128 pushed
 constexpr int SV_PU = 4;                                // lists of one block resolved at a time (independent load chains)
-constexpr int SV_SLOWCAP = 256;                         // blocks per pass that need the general resolution
+constexpr int SV_SLOWCAP = 512;                         // blocks per pass that need the general resolution
 
 struct SieveShared {
 	const uint4* sievePtr[SV_MAXL];                     // group arrays as the sieve counts them: list j repeated mult[j] times
@@ -83,7 +83,7 @@ struct SieveShared {
 	uint32_t bufCount, overflow, query, selPrefixLo, selK;
 	uint32_t nCand, nProbe, nSlow;
 	uint32_t dyn, nGe2, kWant, maxPos, switchGrp;       // dynamic pass (sieve_groups<2, true>): see there
-	uint32_t tim[4];                                    // SV_TIMING: warp 0's cycles >> 6 in the sieve loads, the queue pushes, the resolve rounds
+	uint32_t tim[5];                                    // SV_TIMING: warp 0's cycles >> 6 in the sieve loads, the queue pushes, the resolve rounds
 	uint32_t passG0, passG1, cRej, done;
 	uint32_t qlen, nGrams, cmin, cprom, nLists, sumMult;
 	uint32_t shortActive, scanLong, scanLongOnly;       // read by the shared scoring helpers; always 0 here
@@ -237,8 +237,9 @@ __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t b
 	}
 	if (slow) {
 		// compacted and resolved after the pass, with every lane busy (inline, one such block would stall the whole warp)
+		// (a full queue — a dynamic pass of a query with many lists — does not cost the pass: the block is resolved on the spot)
 		const uint32_t si = atomicAdd(&sh.nSlow, 1u);
-		if (si < SV_SLOWCAP) sh.slowQ[si] = blk; else sh.overflow = 1;
+		if (si < SV_SLOWCAP) sh.slowQ[si] = blk; else resolve_slow(sh, blk, onlyCount, tau);
 		return ns;
 	}
 	// integer pre-filter refined by the block's first id (identity mode: kid == term id >= first id of the block)
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 		}
 		if (tid == 0) {
 			sh.bufCount = 0; sh.overflow = 0; sh.tau = ~0ull; sh.done = 0; sh.nProbe = 0;
-			sh.tim[0] = sh.tim[1] = sh.tim[2] = sh.tim[3] = 0;
+			sh.tim[0] = sh.tim[1] = sh.tim[2] = sh.tim[3] = sh.tim[4] = 0;
 			sh.qlen = d.qlen; sh.nGrams = nGrams; sh.cmin = d.cmin; sh.cprom = d.cprom; sh.nLists = nLists;
 			sh.classMode = classMode;
 			sh.promotedKey = classMode ? 0u : ~float_to_ordered(100.0f);
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 		auto flush_slow = [&](const uint32_t onlyCount) {
 			__syncthreads();
 			const uint32_t n = min(sh.nSlow, (uint32_t)SV_SLOWCAP);
+			if (SV_TIMING && tid == 0) sh.tim[4] += n;
 			// (the count a term needs is the query's own lower bound here, refined per block from tau: the queue holds blocks of
 			// passes with different requirements)
 			if (tid == 0) { sh.defCount = 0; sh.cRej = sh.cmin ? sh.cmin - 1 : 0; }
@@ -654,7 +656,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 				}
 				forceLen = 0;
 				SV_TICK(3);
-				if (tid == 0) { atomicAdd(&counters[26], nCand); }
+				if (tid == 0) { atomicAdd(&counters[26], nCand); sh.tim[3] += nCand; }
 				lastCreq = creq; lastLen = w1 - w0; lastCands = nCand + 1;
 				gLo = w1; lastG1 = w1;
 				level = sh.bufCount;
@@ -710,6 +712,9 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 			if (kc > 1000) atomicAdd(&counters[44], 1u);
 			if (kc > 2000) atomicAdd(&counters[45], 1u);
 			if (kc > 500) atomicAdd(&counters[46], 1u);
+			if (kc > 700 || (q & 127u) == 0)
+				printf("SVQ q=%u kc=%u order=%u nLists=%u nGrams=%u total=%u cand=%u probes=%u slow=%u sieve=%u push=%u resolve=%u\n", q, kc, wi, nLists, nGrams,
+				       d.total, sh.tim[3], sh.nProbe, sh.tim[4], sh.tim[0] >> 4, sh.tim[1] >> 4, sh.tim[2] >> 4);
 		}
 #endif
 	}
