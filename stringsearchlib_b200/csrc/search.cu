@@ -785,6 +785,9 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 			fprintf(stderr, "[ssb] k_sieve_search kilocycles per query: set-up %.1f, plan %.1f, sieve+resolve %.1f, slow+deferred %.1f, select %.1f, final %.1f\n",
 			        hc[32] * 0.064 / hc[6], hc[33] * 0.064 / hc[6], hc[34] * 0.064 / hc[6], hc[35] * 0.064 / hc[6], hc[36] * 0.064 / hc[6], hc[37] * 0.064 / hc[6]),
 			fprintf(stderr, "[ssb]   slowest query %u kilocycles; queries over 0.5 / 1 / 2 megacycles: %u / %u / %u\n", hc[43], hc[46], hc[44], hc[45]),
+			fprintf(stderr, "[ssb]   CTAs by the time they ran out of work (steps of 65.5 us): %u %u %u %u %u %u %u %u %u %u %u %u\n", hc[48], hc[49], hc[50], hc[51],
+			        hc[52], hc[53], hc[54], hc[55], hc[56], hc[57], hc[58], hc[59]),
+			fprintf(stderr, "[ssb]   thread 0's general resolutions: list words %.1f, groups + postings %.1f, counting %.1f kilocycles; %.1f lists hit\n", hc[60] * 0.064 / hc[6], hc[61] * 0.064 / hc[6], hc[62] * 0.064 / hc[6], hc[63] / (double)hc[6]),
 			fprintf(stderr, "[ssb]   of slow+deferred: thread 0's own general resolutions %.1f, waiting for the CTA's %.1f\n", hc[38] * 0.064 / hc[6], hc[39] * 0.064 / hc[6]),
 			fprintf(stderr, "[ssb]   of sieve+resolve, warp 0: loads + counters %.1f, queue pushes %.1f, resolve rounds %.1f\n", hc[40] * 0.064 / hc[6],
 			        hc[41] * 0.064 / hc[6], hc[42] * 0.064 / hc[6]);

@@ -83,7 +83,7 @@ struct SieveShared {
 	uint32_t bufCount, overflow, query, selPrefixLo, selK;
 	uint32_t nCand, nProbe, nSlow;
 	uint32_t dyn, nGe2, kWant, maxPos, switchGrp;       // dynamic pass (sieve_groups<2, true>): see there
-	uint32_t tim[5];                                    // SV_TIMING: warp 0's cycles >> 6 in the sieve loads, the queue pushes, the resolve rounds
+	uint32_t tim[9];                                    // SV_TIMING: warp 0's cycles >> 6 in the sieve loads, the queue pushes, the resolve rounds, ...
 	uint32_t passG0, passG1, cRej, done;
 	uint32_t qlen, nGrams, cmin, cprom, nLists, sumMult;
 	uint32_t shortActive, scanLong, scanLongOnly;       // read by the shared scoring helpers; always 0 here
@@ -142,9 +142,17 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 	// the lists that hit the block (word k of every list's group: independent loads), then per list the postings inside the
 	// block, four in flight at a time
 	uint32_t lm = 0;
+#if SV_TIMING
+	long long ts = clock64();
+#define SV_TICKS(slot) do { if (threadIdx.x == 0) { const long long t_ = clock64(); sh.tim[slot] += (uint32_t)((t_ - ts) >> 6); ts = t_; } } while (0)
+#else
+#define SV_TICKS(slot) do { } while (0)
+#endif
 #pragma unroll 4
 	for (uint32_t j = 0; j < nL; ++j) lm |= ((__ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + g) + 1 + k) >> bit) & 1u) << j;
 	uint32_t ids[CAP], mus[CAP], m = 0;
+	SV_TICKS(5);
+	if (SV_TIMING && threadIdx.x == 0) sh.tim[8] += __popc(lm);
 	while (lm) {
 		const uint32_t j = (uint32_t)__ffs(lm) - 1u;
 		lm &= lm - 1;
@@ -168,6 +176,7 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 		}
 		if (!any) sh.overflow = 2;                           // bitmap and postings disagree: never trust, hand the query over
 	}
+	SV_TICKS(6);
 	for (uint32_t a = 0; a < m; ++a) {
 		uint32_t c = 0;
 		bool first = true;
@@ -175,6 +184,7 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 			if (ids[b] == ids[a]) { if (b < a) first = false; c += mus[b]; }
 		if (first && c > cRej && (!onlyCount || c == onlyCount)) sieve_emit(sh, ids[a], c, tau);
 	}
+	SV_TICKS(7);
 }
 
 // ---- RESOLVE one block that passed the sieve (one thread per block, a full warp of blocks at a time). Returns the number
@@ -424,13 +434,26 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 		sh.shortActive = 0; sh.scanLong = 0; sh.scanLongOnly = 0; sh.threshold = threshold;
 	}
 
+#if SV_TIMING
+	unsigned long long gt0, gtq = 0; uint32_t nDone = 0;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+#endif
 	while (true) {
 		__syncthreads();
 		if (tid == 0) sh.query = atomicAdd(&counters[2], 1u);
 		__syncthreads();
 		const uint32_t wi = sh.query;
+#if SV_TIMING
+		if (wi >= nFast) {
+			unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+			// when the CTAs run out of work: histogram of (end - start) in steps of 65.5 us in counters[48..59]
+			if (tid == 0) atomicAdd(&counters[48 + min((uint32_t)((gt1 - gt0) >> 16), 11u)], 1u);
+			(void)gtq; (void)nDone;
+		}
+#endif
 		if (wi >= nFast) break;
 #if SV_TIMING
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gtq)); ++nDone;
 		long long tick = clock64();
 		const long long tQuery = tick;
 #endif
@@ -473,7 +496,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 		}
 		if (tid == 0) {
 			sh.bufCount = 0; sh.overflow = 0; sh.tau = ~0ull; sh.done = 0; sh.nProbe = 0;
-			sh.tim[0] = sh.tim[1] = sh.tim[2] = sh.tim[3] = sh.tim[4] = 0;
+			for (int i = 0; i < 9; ++i) sh.tim[i] = 0;
 			sh.qlen = d.qlen; sh.nGrams = nGrams; sh.cmin = d.cmin; sh.cprom = d.cprom; sh.nLists = nLists;
 			sh.classMode = classMode;
 			sh.promotedKey = classMode ? 0u : ~float_to_ordered(100.0f);
@@ -705,6 +728,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 		SV_TICK(5);
 #if SV_TIMING
 		if (tid == 0) {
+			atomicAdd(&counters[60], sh.tim[5]); atomicAdd(&counters[61], sh.tim[6]); atomicAdd(&counters[62], sh.tim[7]); atomicAdd(&counters[63], sh.tim[8]);
 			atomicAdd(&counters[40], sh.tim[0]); atomicAdd(&counters[41], sh.tim[1]); atomicAdd(&counters[42], sh.tim[2]);
 			// the slowest query of the batch, the number of queries over 1 and 2 megacycles, and when the last query started / ended
 			const uint32_t kc = (uint32_t)((clock64() - tQuery) >> 10);
@@ -712,7 +736,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 			if (kc > 1000) atomicAdd(&counters[44], 1u);
 			if (kc > 2000) atomicAdd(&counters[45], 1u);
 			if (kc > 500) atomicAdd(&counters[46], 1u);
-			if (kc > 700 || (q & 127u) == 0)
+			if (SV_TIMING >= 2 && (kc > 700 || (q & 127u) == 0))
 				printf("SVQ q=%u kc=%u order=%u nLists=%u nGrams=%u total=%u cand=%u probes=%u slow=%u sieve=%u push=%u resolve=%u\n", q, kc, wi, nLists, nGrams,
 				       d.total, sh.tim[3], sh.nProbe, sh.tim[4], sh.tim[0] >> 4, sh.tim[1] >> 4, sh.tim[2] >> 4);
 		}
