@@ -232,6 +232,15 @@ def main():
         tb = torch.tensor([t_build], device="cuda")
         dist.all_reduce(tb, op=dist.ReduceOp.MAX)
         t_build = float(tb.item())
+    # getSize / getLibSize of the whole index: distinct terms and grams over all shards (SURVEY.md §8e "Global counters")
+    global_sizes = None
+    if world > 1 and not replicas:
+        barrier()
+        t0 = time.perf_counter()
+        gs = api.global_sizes(ix, dist)
+        barrier()
+        global_sizes = {"getSize": gs[0], "getLibSize": gs[1], "seconds": time.perf_counter() - t0,
+                        "how": "16-byte digests per term / gram, all-gather, distinct count per residue class on every rank, all-reduce"}
 
     nsteps = args.warmup + args.steps
     nb = args.batch // world if replicas else args.batch          # queries this rank answers per step
@@ -470,6 +479,8 @@ def main():
                             "device_only_keys_per_s": (hi - lo) / max((bms["total"] - bms["pack"]) / 1e3, 1e-9),
                             "terms": info["T"], "grams": info["G"], "postings": info["P"], "device_bytes": info["deviceBytes"]},
             "host_cores": cores}
+    if global_sizes:
+        line["index_build"]["global_sizes"] = global_sizes
     if exch_ms:
         line["exchange_ms_per_step"] = float(np.mean(exch_ms))      # device time of export + cross-shard merge (max over ranks), part of ms_per_step
     if world == 1 and not args.no_cpu_baseline:

@@ -18,7 +18,7 @@ OBJ = os.path.join(ROOT, "build", "obj")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"] + ARCH + os.environ.get("SSB_NVCC_FLAGS", "").split()
-CU = ["primitives.cu", "build.cu", "sieve.cu", "search.cu", "merge.cu", "engine.cu"]
+CU = ["primitives.cu", "build.cu", "sieve.cu", "search.cu", "merge.cu", "digest.cu", "engine.cu"]
 
 
 def newer(src_list, out):

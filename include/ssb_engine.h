@@ -129,6 +129,19 @@ int ssb_merge_records_p2p_wait(const void* d_recv, uint32_t nShards, uint32_t nq
                                void* const* peerCounts, uint32_t nOut, uint32_t myRank, const void* d_myFlags, uint32_t epoch);
 int ssb_device_memset(void* d_ptr, int value, uint64_t bytes);
 
+/* ---- global getSize / getLibSize over key-range shards (SURVEY.md §8e "Global counters"; nGramSearch.hpp:488-499).
+ * Both are DISTINCT counts (terms, grams) and the same term or gram can live in several shards: the global value is the
+ * size of a union. Every shard exports one 16-byte digest per term (which = 0) or gram (which = 1) — grams packed exactly
+ * from their code units when g units fit 128 bits, two independent 64-bit hashes otherwise (digest.cu) — the digests of all
+ * shards are gathered into one device array (all-gather / peer copies: the caller's plumbing, like the record exchange),
+ * every rank counts the distinct digests of residue class `part` of `nParts` (equal digests share a class) and the counts
+ * are summed. One process: nParts = 1 over the concatenated digests of its shards.
+ * ssb_index_digest_count: digests the shard exports. ssb_index_export_digests: d_out = device memory, count * 16 bytes;
+ * returns synchronised. ssb_count_distinct_digests: *out = the number; returns synchronised. 0 on success. */
+uint64_t ssb_index_digest_count(const ssb_index* ix, int which);
+int ssb_index_export_digests(ssb_index* ix, int which, void* d_out);
+int ssb_count_distinct_digests(const void* d_digests, uint64_t n, uint32_t part, uint32_t nParts, uint64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,5 +7,5 @@ mkdir -p build/variants build/vobj
 nvcc -std=c++17 -O3 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -gencode arch=compute_100a,code=sm_100a "$@" \
   -c stringsearchlib_b200/csrc/search.cu -o build/vobj/search_$name.o
 nvcc -shared -cudart static -o build/variants/$name.so build/obj/primitives.o build/obj/build.o build/obj/sieve.o build/vobj/search_$name.o \
-  build/obj/merge.o build/obj/engine.o -gencode arch=compute_100a,code=sm_100a
+  build/obj/merge.o build/obj/digest.o build/obj/engine.o -gencode arch=compute_100a,code=sm_100a
 echo built build/variants/$name.so

@@ -77,6 +77,10 @@ def core_library():
     lib.ssb_merge_records_p2p_wait.argtypes = [c_void_p, c_uint32, c_uint32, c_uint32, POINTER(c_void_p), POINTER(c_void_p), c_uint32, c_uint32,
                                                c_void_p, c_uint32]
     lib.ssb_device_memset.argtypes = [c_void_p, c_int, c_uint64]
+    lib.ssb_index_digest_count.restype = c_uint64
+    lib.ssb_index_digest_count.argtypes = [c_void_p, c_int]
+    lib.ssb_index_export_digests.argtypes = [c_void_p, c_int, c_void_p]
+    lib.ssb_count_distinct_digests.argtypes = [c_void_p, c_uint64, c_uint32, c_uint32, POINTER(c_uint64)]
     lib.ssb_search_one.argtypes = [c_void_p, c_void_p, c_float, c_uint32]
     lib.ssb_search_one.restype = POINTER(_Batch)
     lib.ssb_search_one_stats.argtypes = [c_void_p, POINTER(c_uint64)]
@@ -360,6 +364,13 @@ class Index:
         _check(self._lib.ssb_export_records_p2p_signal(self._h, nq, limit, _ptr_list(peer_recv), len(peer_recv), rank,
                                                        _ptr_list(peer_flags), epoch))
 
+    def digest_count(self, which):
+        """16-byte digests this shard exports: which 0 = terms (getSize), 1 = grams (getLibSize)."""
+        return int(self._lib.ssb_index_digest_count(self._h, which))
+
+    def export_digests(self, which, device_ptr):
+        _check(self._lib.ssb_index_export_digests(self._h, which, device_ptr))
+
     def export_records(self, nq, limit, device_ptr):
         if self._lib.ssb_export_records(self._h, nq, limit, device_ptr) != 0:
             raise RuntimeError(self._lib.ssb_last_error().decode())
@@ -418,6 +429,45 @@ def merge_records_p2p_wait(recv_ptr, n_shards, nq_local, limit, out_merged, out_
 
 def device_memset(ptr, value, nbytes):
     _check(core_library().ssb_device_memset(ptr, int(value), int(nbytes)))
+
+
+def count_distinct_digests(digests_ptr, n, part=0, n_parts=1):
+    """distinct 16-byte digests among n at digests_ptr (device) whose residue class is `part` of `n_parts`."""
+    out = c_uint64(0)
+    _check(core_library().ssb_count_distinct_digests(digests_ptr, int(n), part, n_parts, ctypes.byref(out)))
+    return int(out.value)
+
+
+def global_sizes(ix, dist=None, device=None):
+    """(getSize, getLibSize) of the whole index when `ix` is this rank's key-range shard: distinct terms
+    and grams over all shards. dist = torch.distributed with an initialised process group (None: one shard = the shard's own
+    numbers). One all-gather of the digest counts, one of the padded digests and one 8-byte all-reduce per counter."""
+    import torch
+    if dist is None or dist.get_world_size() == 1:
+        return ix.size(), ix.lib_size()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+    out = []
+    for which in (0, 1):
+        n = ix.digest_count(which)
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        mine_n = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, mine_n)
+        counts = counts.cpu().tolist()
+        cap = max(max(counts), 1)
+        mine = torch.zeros((cap, 16), dtype=torch.uint8, device=dev)
+        if n:
+            ix.export_digests(which, mine.data_ptr())
+        gathered = torch.empty((world, cap, 16), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, mine)
+        # drop the padding: the shards' digests back to back
+        flat = torch.cat([gathered[r, :counts[r]] for r in range(world)]).contiguous()
+        torch.cuda.synchronize()
+        part = count_distinct_digests(flat.data_ptr(), flat.shape[0], rank, world) if flat.shape[0] else 0
+        t = torch.tensor([part], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        out.append(int(t.item()))
+    return out[0], out[1]
 
 
 def merge_records(gathered_ptr, n_shards, nq, limit, merged_ptr, counts_ptr):

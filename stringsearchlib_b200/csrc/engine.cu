@@ -4,6 +4,7 @@
 #include "../../include/ssb_engine.h"
 #include "index.h"
 #include "search.h"
+#include "digest.h"
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -788,6 +789,30 @@ SSB_API int ssb_merge_records(const void* d_gathered, uint32_t nShards, uint32_t
 		g_engine.init();
 		// asynchronous on the legacy default stream: ordered behind collectives the caller enqueued there (torch's default)
 		merge_records(static_cast<const MergeRecord*>(d_gathered), nShards, nq, limit, static_cast<MergeRecord*>(d_merged), d_counts, 0);
+		return 0;
+	}, -1);
+}
+
+SSB_API uint64_t ssb_index_digest_count(const ssb_index* ix, int which)
+{
+	return ix && (which == 0 || which == 1) ? digest_count(ix->dix, which) : 0;
+}
+SSB_API int ssb_index_export_digests(ssb_index* ix, int which, void* d_out)
+{
+	if (!ix || (which != 0 && which != 1)) return -1;
+	return guarded([&] {
+		g_engine.init();
+		std::lock_guard<std::mutex> lk(ix->mu);
+		export_digests(ix->dix, which, d_out, ix->stream);
+		return 0;
+	}, -1);
+}
+SSB_API int ssb_count_distinct_digests(const void* d_digests, uint64_t n, uint32_t part, uint32_t nParts, uint64_t* out)
+{
+	if (!out) return -1;
+	return guarded([&] {
+		g_engine.init();
+		*out = count_distinct_digests(d_digests, n, part, nParts, 0);
 		return 0;
 	}, -1);
 }

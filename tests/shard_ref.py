@@ -55,3 +55,28 @@ def merge_records(gathered, limit):
         for i, c in enumerate(top):
             out[q, i] = c[3]
     return out, counts
+
+
+# ---- global getSize / getLibSize over shards (SURVEY.md §8e "Global counters"): the protocol of stringsearchlib_b200/csrc/digest.cu
+# in numpy — 16-byte digests per term / gram, distinct count per residue class, sum over the classes
+def digests_of(units_2d_or_list):
+    """16-byte digests (numpy void16) of unit sequences; any injective-enough function works for the protocol test."""
+    import hashlib
+    out = np.zeros(len(units_2d_or_list), dtype="V16")
+    for i, u in enumerate(units_2d_or_list):
+        out[i] = hashlib.blake2b(np.asarray(u, dtype=np.uint32).tobytes(), digest_size=16).digest()
+    return out
+
+
+def count_distinct_part(digests, part, n_parts):
+    """distinct digests whose residue class is `part` (equal digests share a class)."""
+    if len(digests) == 0:
+        return 0
+    lo = np.frombuffer(digests.tobytes(), dtype=np.uint64).reshape(-1, 2)[:, 0]
+    sel = digests[(lo % np.uint64(n_parts)) == np.uint64(part)]
+    return len(np.unique(sel))
+
+
+def spec_terms(tables):
+    off = tables["termOff"].astype(np.int64)
+    return [tables["termChars"][off[i]:off[i + 1]] for i in range(len(off) - 1)]

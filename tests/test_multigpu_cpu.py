@@ -84,3 +84,54 @@ def test_merge_collapses_equal_keys_across_shards():
     assert c[0] == 3
     assert [int(x) for x in m["hash"][0]] == [111, 222, 333]
     assert m["scoreBits"][0, 0] == f(0.75)
+
+
+def _sizes_worker(rank, world, port, rows, rs, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from oracle import loader
+    from shard_ref import count_distinct_part, digests_of, shard_bounds, spec_terms
+    from util import random_corpus
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    words, w = random_corpus(np.random.default_rng(5), rows, rs, weighted=True, max_len=14)
+    b = shard_bounds(rows, world)
+    lo, hi = b[rank] * rs, b[rank + 1] * rs
+    S = loader.SpecIndex(words[lo:hi], rs, w[lo:hi], 3, False, row_base=b[rank])
+    t = S.tables()
+    res = []
+    for mine in (digests_of(spec_terms(t)), digests_of(list(t["gramUnits"]))):
+        # all-gather of the counts, then of the padded digests (what api.global_sizes does with NCCL)
+        counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([len(mine)], dtype=torch.int64))
+        counts = [int(c) for c in counts]
+        cap = max(max(counts), 1)
+        pad = np.zeros((cap, 16), np.uint8)
+        pad[:len(mine)] = np.frombuffer(mine.tobytes(), np.uint8).reshape(-1, 16)
+        gathered = [torch.zeros((cap, 16), dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(pad))
+        flat = np.concatenate([g.numpy()[:c] for g, c in zip(gathered, counts)])
+        flat = np.frombuffer(flat.tobytes(), dtype="V16")
+        part = torch.tensor([count_distinct_part(flat, rank, world)], dtype=torch.int64)
+        dist.all_reduce(part)
+        res.append((int(part), sum(counts)))
+    np.save(os.path.join(out_dir, f"sizes_{rank}.npy"), np.array(res, np.int64))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_global_sizes_equal_unsharded(oracle_built, tmp_path):
+    """getSize / getLibSize over two key-range shards = the unsharded oracle's (SURVEY.md §8e "Global counters")."""
+    import torch.multiprocessing as mp
+    from util import random_corpus
+    rows, rs, world = 3000, 2, 2
+    mp.spawn(_sizes_worker, args=(world, _free_port(), rows, rs, str(tmp_path)), nprocs=world, join=True)
+    words, w = random_corpus(np.random.default_rng(5), rows, rs, weighted=True, max_len=14)
+    S = oracle_built.SpecIndex(words, rs, w)
+    r0, r1 = np.load(tmp_path / "sizes_0.npy"), np.load(tmp_path / "sizes_1.npy")
+    assert np.array_equal(r0, r1)
+    assert (int(r0[0, 0]), int(r0[1, 0])) == (S.size(), S.lib_size())
+    assert r0[0, 1] > r0[0, 0] and r0[1, 1] > r0[1, 0]          # terms and grams are shared between the shards: sums overcount

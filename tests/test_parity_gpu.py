@@ -425,6 +425,53 @@ def test_key_range_shards_p2p_signal_wait(ssb, oracle_built):
         api.device_free(p)
 
 
+def test_global_sizes_over_shards(ssb, oracle_built):
+    """getSize / getLibSize of a sharded index (SURVEY.md §8e "Global counters", nGramSearch.hpp:488-499): the distinct terms
+    and grams over all key-range shards — digests gathered, counted per residue class, summed — equal the unsharded index's
+    and the oracle's numbers. Corpora with many terms and grams shared between shards; narrow and wide; gSize 2, 3 and 5."""
+    import torch
+    from stringsearchlib_b200 import synth
+    from stringsearchlib_b200.api import count_distinct_digests
+    rng = np.random.default_rng(11)
+    messy, w = random_corpus(rng, 4000, 2, weighted=True, max_len=14)
+    wide = synth.wide_keys(20000)
+    wide_dup = [wide.get(i) for i in list(range(12000)) + list(range(3000, 9000))]            # rows 12000.. repeat rows 3000..
+    ascii_dup = [synth.ascii_keys(9000).get(i) for i in list(range(9000)) + list(range(0, 9000, 3))]
+    cases = [(messy, 2, w, 3, False), (messy, 2, w, 2, False), (wide_dup, 1, None, 2, True), (ascii_dup, 1, None, 3, False),
+             (ascii_dup, 1, None, 5, False)]
+    for words, rs, weights, g, is_wide in cases:
+        S = oracle_built.SpecIndex(words, rs, weights, g, is_wide)
+        rows = len(words) // rs
+        with ssb.Index(words, rs, weights, g, wide=is_wide) as whole:
+            assert (whole.size(), whole.lib_size()) == (S.size(), S.lib_size())
+        for shards in (2, 3):
+            bounds = np.linspace(0, rows, shards + 1).astype(int)
+            idx = []
+            for sh in range(shards):
+                lo, hi = int(bounds[sh]) * rs, int(bounds[sh + 1]) * rs
+                idx.append(ssb.Index(words[lo:hi], rs, None if weights is None else weights[lo:hi], g, wide=is_wide, row_base=int(bounds[sh])))
+            got = []
+            for which in (0, 1):
+                counts = [ix.digest_count(which) for ix in idx]
+                assert counts == [ix.size() if which == 0 else ix.lib_size() for ix in idx]
+                buf = torch.zeros((max(sum(counts), 1), 16), dtype=torch.uint8, device="cuda")
+                at = 0
+                for ix, c in zip(idx, counts):
+                    if c:
+                        ix.export_digests(which, buf[at:].data_ptr())
+                    at += c
+                torch.cuda.synchronize()
+                one = count_distinct_digests(buf.data_ptr(), at)
+                parts = [count_distinct_digests(buf.data_ptr(), at, p, 3) for p in range(3)]
+                assert sum(parts) == one and (at < 100 or all(parts))
+                got.append(one)
+            for ix in idx:
+                ix.close()
+            assert tuple(got) == (S.size(), S.lib_size()), (rs, g, is_wide, shards, got, sum(counts))
+            if shards == 2:
+                assert sum(counts) > got[1]          # the shards do share grams: a sum would be wrong
+
+
 def test_merge_collapses_duplicates_and_large_limit(ssb, oracle_built):
     """the same key strings in several shards collapse to one entry (best score); 8 shards x limit 1000 exercises the
     hierarchical merge (more records than one CTA's shared memory holds)."""
