@@ -97,7 +97,7 @@ def reference_leg(args, nkeys_sample, nq_sample, threads, steps=1, warmup=0):
     t_build = time.perf_counter() - t0
     L = R.L
 
-    def run_batch(q):
+    def run_batch(q, threads=threads):
         ptrs = q.pointers()
         nq = len(q)
         addr = ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_char_p))
@@ -126,9 +126,12 @@ def reference_leg(args, nkeys_sample, nq_sample, threads, steps=1, warmup=0):
         dt, _ = run_batch(q)
         if s >= warmup:
             times.append(dt)
+    # (i) one caller thread next to (ii) all host threads — the first queries of the same sample
+    n1 = max(8, nq_sample // max(threads, 1))
+    dt1, _ = run_batch(synth.ascii_queries(n1, nkeys_sample), threads=1)
     R.dispose(h)
     qps = nq_sample * len(times) / sum(times)
-    return dict(qps=qps, build_keys_per_s=nkeys_sample / t_build, build_s=t_build, ms_per_step=1e3 * sum(times) / len(times))
+    return dict(qps=qps, qps_one_thread=n1 / dt1, build_keys_per_s=nkeys_sample / t_build, build_s=t_build, ms_per_step=1e3 * sum(times) / len(times))
 
 
 def main():
@@ -183,7 +186,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["qps"], "unit": "queries/s", "cores": threads, "kind": "reference", "sample": sample},
-                "index_build_keys_per_s": r["build_keys_per_s"],
+                "index_build_keys_per_s": r["build_keys_per_s"], "one_thread_value": r["qps_one_thread"],
                 "e2e": {"value": r["qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -489,7 +492,7 @@ def main():
             line["cpu_baseline"] = {"value": cb["qps"], "unit": "queries/s", "cores": cores, "kind": "reference",
                                     "sample": f"unmodified reference (oracle/_ref): indexN over the first {args.cpu_keys} keys, "
                                               f"{min(args.cpu_queries, args.batch)} queries via score()/release(), {cores} threads",
-                                    "index_build_keys_per_s": cb["build_keys_per_s"]}
+                                    "index_build_keys_per_s": cb["build_keys_per_s"], "one_thread_value": cb["qps_one_thread"]}
         except Exception as e:  # the reference .so is test infrastructure; its absence must not hide the GPU numbers
             line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": cores, "kind": "reference", "sample": f"unavailable: {e}"}
     print(json.dumps(line))
