@@ -63,6 +63,11 @@ def build(force=False, verbose=False):
         if force or jobs or newer([srcp] + headers, out):
             run(["g++", "-std=c++17", "-O2", "-fPIC", "-fvisibility=hidden", "-shared", "-pthread", srcp, "-o", out,
                  "-L" + LIB, "-lssb_core", "-Wl,-rpath,$ORIGIN", "-lstdc++"])
+    # micro-benchmark behind bench.py's random-access figure (not part of the product)
+    micro = os.path.join(ROOT, "scripts", "micro", "random_sectors.cu")
+    mout = os.path.join(LIB, "random_sectors")
+    if force or newer([micro], mout):
+        run([NVCC, "-O3", "-lineinfo"] + ARCH + ["-o", mout, micro])
     if verbose:
         for f in CU:
             log = os.path.join(OBJ, f.replace(".cu", ".o.log"))

@@ -353,7 +353,7 @@ class Index:
         if self._lib.ssb_search_resident(self._h, nq, threshold, limit, ms, st) != 0:
             raise RuntimeError(self._lib.ssb_last_error().decode())
         return ms[0], ms[1], dict(nFast=int(st[0]), nDense=int(st[1]), nOverflow=int(st[2]), postings=int(st[3]),
-                                  nSieve=int(st[4]), nSieveHandover=int(st[5]), nSieveGiveUp=int(st[6]))
+                                  nSieve=int(st[4]), nSieveHandover=int(st[5]), nSieveGiveUp=int(st[6]), sieveProbes=int(st[7]))
 
     def export_records_p2p(self, nq, limit, peer_recv, rank):
         """fused export + exchange: query q's records go straight into peer_recv[q // (nq/N)] (peer-mapped pointers)."""

@@ -766,7 +766,7 @@ SSB_API int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uin
 		if (ms) { ms[0] = st.msDevice; ms[1] = st.msFastKernel; }
 		if (stats) {
 			stats[0] = st.nFast; stats[1] = st.nDense; stats[2] = st.nOverflow; stats[3] = st.postingsTouched;
-			stats[4] = st.nSieve; stats[5] = st.nSieveHandover; stats[6] = st.nSieveGiveUp; stats[7] = 0;
+			stats[4] = st.nSieve; stats[5] = st.nSieveHandover; stats[6] = st.nSieveGiveUp; stats[7] = st.sieveProbes;
 		}
 		return 0;
 	}, -1);

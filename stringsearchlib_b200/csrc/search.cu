@@ -773,7 +773,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	}
 	if (st) {
 		st->nFast = nFast; st->nDense = nDense; st->nOverflow = nOverflow;
-		st->nSieve = hc[6]; st->nSieveHandover = hc[5]; st->nSieveGiveUp = hc[28];
+		st->nSieve = hc[6]; st->nSieveHandover = hc[5]; st->nSieveGiveUp = hc[28]; st->sieveProbes = hc[25];
 		static const bool dbg = getenv("SSB_DEBUG") != nullptr;
 		if (dbg && nFast)
 			fprintf(stderr, "[ssb] k_fast_search per query: %.1f passes, %.2f redone, %.1f selects, %.1f deferred evaluations\n", hc[16] / (double)nFast,
