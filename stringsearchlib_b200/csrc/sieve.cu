@@ -3,12 +3,15 @@
 // The reference counts matches by touching every posting of every query gram (nGramSearch.hpp:289-298). Once the running
 // k-th best or the threshold (hpp:313-316) demands c matches, a term can only matter if it lies in a BLOCK of 2^shift
 // consecutive term ids in which at least c of the query's lists have a posting. For every gram with a long enough list
-// this file derives from the (bit-exact) CSR postings one array of 16-byte GROUPS, 96 blocks each:
+// this file derives from the (bit-exact) CSR postings one array of GROUPS, 96 blocks each:
 //   { first, bits0, bits1, bits2 }   first = absolute index of the list's first posting at or after the group's first block,
 //                                    bits  = one bit per block: the list has a posting in the block
-// so that a query streams K such arrays (K * T / 2^shift / 6 bytes) through a bit-sliced threshold counter and only reads
-// the postings of the few blocks that pass it: first + popcount of the lower bits of the same 16 bytes is the position of the
-// block's first posting. Derived data: rebuilt after ssb_index_load, never serialised, never compared by the parity tests —
+//   { 128 bits of slots }            (SSB_SIEVE_INLINE, index.h) per occupied block, in order: offset of its first posting inside
+//                                    the block + "more postings follow in this block"
+// so that a query streams K such arrays through a bit-sliced threshold counter and resolves the few blocks that pass it from
+// the same 32-byte sector: block number + slot offset is the term id. Only blocks in which a list has several postings (or
+// groups with more occupied blocks than slots) go back to the postings: first + popcount of the lower bits is the position
+// of the block's first posting. Derived data: rebuilt after ssb_index_load, never serialised, never compared by the parity tests —
 // postings stay the source of truth.
 #include "index.h"
 #include "primitives.cuh"
@@ -55,11 +58,12 @@ __global__ void __launch_bounds__(TPB) k_sieve_fill(const uint32_t* __restrict__
 	const uint32_t slot = blockIdx.x;
 	const uint32_t g = gramOfSlot[slot];
 	const uint32_t lo = gramOff[g], hi = gramOff[g + 1];
-	uint32_t* mine = groups + (size_t)slot * nGroups * 4;
+	constexpr uint32_t W = 4 * SIEVE_GROUP_U4;                             // 32-bit words per group
+	uint32_t* mine = groups + (size_t)slot * nGroups * W;
 	for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
 		const uint32_t b = postings[i] >> shift;
 		const uint32_t v = b >> 5, gr = v / 3u, k = v - 3u * gr;            // virtual word v = 3 * group + k
-		atomicOr(&mine[(size_t)gr * 4 + 1 + k], 1u << (b & 31));
+		atomicOr(&mine[(size_t)gr * W + 1 + k], 1u << (b & 31));
 	}
 	for (uint32_t gr = threadIdx.x; gr < nGroups; gr += blockDim.x) {
 		const unsigned long long firstId = ((unsigned long long)gr * SIEVE_GROUP_BLOCKS) << shift;
@@ -68,8 +72,26 @@ __global__ void __launch_bounds__(TPB) k_sieve_fill(const uint32_t* __restrict__
 			const uint32_t m = a + ((z - a) >> 1);
 			if ((unsigned long long)postings[m] < firstId) a = m + 1; else z = m;
 		}
-		mine[(size_t)gr * 4] = a;
+		mine[(size_t)gr * W] = a;
 	}
+#if SSB_SIEVE_INLINE
+	__syncthreads();                                                       // the bits of this list are complete
+	const uint32_t bps = sieve_slot_bits(shift), nSlot = sieve_slots_per_group(shift);
+	for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+		const uint32_t id = postings[i], b = id >> shift;
+		if (i > lo && (postings[i - 1] >> shift) == b) continue;           // not the block's first posting
+		const uint32_t multi = (i + 1 < hi && (postings[i + 1] >> shift) == b) ? 1u : 0u;
+		const uint32_t v = b >> 5, gr = v / 3u, k = v - 3u * gr, bit = b & 31u;
+		const uint32_t* w = mine + (size_t)gr * W;
+		const uint32_t r = (k > 0 ? __popc(w[1]) : 0) + (k > 1 ? __popc(w[2]) : 0) + __popc(w[1 + k] & ((1u << bit) - 1u));
+		if (r >= nSlot) continue;                                          // (k_sieve_search sends such blocks to the postings)
+		const unsigned long long val = (unsigned long long)((multi << shift) | (id & ((1u << shift) - 1u)));
+		const uint32_t at = r * bps, wd = at >> 5, sh = at & 31u;
+		const unsigned long long sv = val << sh;
+		atomicOr(&mine[(size_t)gr * W + 4 + wd], (uint32_t)sv);
+		if ((uint32_t)(sv >> 32)) atomicOr(&mine[(size_t)gr * W + 4 + wd + 1], (uint32_t)(sv >> 32));
+	}
+#endif
 }
 
 }   // namespace
@@ -97,7 +119,7 @@ void build_sieve(DeviceIndex& ix, cudaStream_t s)
 	shift = std::max(0, std::min(shift, 20));
 	const uint64_t nBlocks = (((uint64_t)ix.T - 1) >> shift) + 1;
 	const uint64_t nGroups = (nBlocks + SIEVE_GROUP_BLOCKS - 1) / SIEVE_GROUP_BLOCKS;
-	// a gram gets a bitmap when the bitmap (16 bytes per group) is at most twice as large as its posting list — or always,
+	// a gram gets a bitmap when its block bits (16 bytes per group) are at most twice as large as its posting list — or always,
 	// on indexes so small that bitmaps for every gram stay within that budget overall
 	uint32_t minLen = (uint32_t)std::max<uint64_t>(1, 2 * nGroups);
 	if ((uint64_t)ix.G * nGroups * 4 <= 2ull * ix.P + (1u << 18)) minLen = 1;
@@ -115,7 +137,7 @@ void build_sieve(DeviceIndex& ix, cudaStream_t s)
 	ix.sieveSlot.alloc(ix.G, s);
 	k_sieve_slots<<<grid_for(ix.G), TPB, 0, s>>>(flag.get(), pos.get(), ix.G, ix.sieveSlot.get(), gramOfSlot.get());
 	SSB_LAUNCH_CHECK();
-	ix.sieveGroups.alloc((size_t)nSlots * nGroups * 4, s);
+	ix.sieveGroups.alloc((size_t)nSlots * nGroups * 4 * SIEVE_GROUP_U4, s);
 	ix.sieveGroups.zero(s);
 	k_sieve_fill<<<nSlots, TPB, 0, s>>>(gramOfSlot.get(), ix.gramOff.get(), ix.postings.get(), shift, (uint32_t)nGroups, ix.sieveGroups.get());
 	SSB_LAUNCH_CHECK();

@@ -149,7 +149,7 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 #define SV_TICKS(slot) do { } while (0)
 #endif
 #pragma unroll 4
-	for (uint32_t j = 0; j < nL; ++j) lm |= ((__ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + g) + 1 + k) >> bit) & 1u) << j;
+	for (uint32_t j = 0; j < nL; ++j) lm |= ((__ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + SIEVE_GROUP_U4 * g) + 1 + k) >> bit) & 1u) << j;
 	uint32_t ids[CAP], mus[CAP], m = 0;
 	SV_TICKS(5);
 	if (SV_TIMING && threadIdx.x == 0) sh.tim[8] += __popc(lm);
@@ -157,7 +157,7 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 		const uint32_t j = (uint32_t)__ffs(lm) - 1u;
 		lm &= lm - 1;
 		uint32_t p;
-		sieve_locate(__ldg(sh.grpPtr[j] + g), k, bit, p);
+		sieve_locate(__ldg(sh.grpPtr[j] + SIEVE_GROUP_U4 * g), k, bit, p);
 		const uint32_t end = sh.listEnd[j], mu = sh.mult[j];
 		bool any = false, more = true;
 		while (more && p < end) {
@@ -204,13 +204,57 @@ __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t b
 		uint32_t wv[SV_MAXL];
 #pragma unroll
 		for (int j = 0; j < SV_MAXL; ++j)
-			wv[j] = (uint32_t)j < nL ? __ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + g) + 1 + k) : 0u;
+			wv[j] = (uint32_t)j < nL ? __ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + SIEVE_GROUP_U4 * g) + 1 + k) : 0u;
 #pragma unroll
 		for (int j = 0; j < SV_MAXL; ++j) lm |= ((wv[j] >> bit) & 1u) << j;
 	}
 	const uint32_t ns = __popc(lm);
 	const uint32_t low = (1u << bit) - 1u;
 	const uint32_t my = k == 0 ? low : 0xFFFFFFFFu, mz = k == 1 ? low : (k > 1 ? 0xFFFFFFFFu : 0u), mw = k == 2 ? low : 0u;
+#if SSB_SIEVE_INLINE
+	// (2) the group of the first SV_PU lists that hit: the block's rank among the group's occupied blocks, then (3) that slot of
+	// the same 32-byte sector (it has just arrived): the offset of the list's posting inside the block — block number + offset is
+	// the term id, no posting is read. A block in which the list has several postings, or whose slot did not fit, is left to
+	// the general resolution.
+	bool slow = ns > SV_PU;
+	uint32_t h[SV_PU], mu[SV_PU], rk[SV_PU], jp = 0;
+	const uint32_t bps = sieve_slot_bits(shift), nSlot = sieve_slots_per_group(shift);
+	{
+		uint4 x[SV_PU];
+		uint32_t rest = lm;
+#pragma unroll
+		for (int u = 0; u < SV_PU; ++u) {
+			const uint32_t j = rest ? (uint32_t)__ffs(rest) - 1u : 0u;
+			x[u] = rest ? __ldg(sh.grpPtr[j] + SIEVE_GROUP_U4 * g) : make_uint4(0, 0, 0, 0);
+			jp |= j << (4 * u);
+			rest &= rest - 1;
+		}
+#pragma unroll
+		for (int u = 0; u < SV_PU; ++u) rk[u] = __popc(x[u].y & my) + __popc(x[u].z & mz) + __popc(x[u].w & mw);
+	}
+	{
+		uint32_t s0[SV_PU], s1[SV_PU];
+#pragma unroll
+		for (int u = 0; u < SV_PU; ++u) {
+			const uint32_t j = (jp >> (4 * u)) & 15u;
+			const bool on = (uint32_t)u < ns && rk[u] < nSlot;
+			const uint32_t wd = (rk[u] * bps) >> 5;
+			const uint32_t* sp = reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + SIEVE_GROUP_U4 * g + 1);
+			s0[u] = on ? __ldg(sp + wd) : 0u;
+			s1[u] = on && wd < 3 ? __ldg(sp + wd + 1) : 0u;
+			mu[u] = sh.mult[j];
+		}
+#pragma unroll
+		for (int u = 0; u < SV_PU; ++u) {
+			const uint32_t v = __funnelshift_r(s0[u], s1[u], (rk[u] * bps) & 31u) & ((1u << bps) - 1u);
+			h[u] = INF;
+			if ((uint32_t)u < ns) {
+				if (rk[u] < nSlot && !(v >> shift)) h[u] = (blk << shift) | v;
+				else slow = true;
+			}
+		}
+	}
+#else
 	uint32_t idx[SV_PU], jp = 0;
 	{
 		uint4 x[SV_PU];
@@ -218,7 +262,7 @@ __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t b
 #pragma unroll
 		for (int u = 0; u < SV_PU; ++u) {
 			const uint32_t j = rest ? (uint32_t)__ffs(rest) - 1u : 0u;
-			x[u] = rest ? __ldg(sh.grpPtr[j] + g) : make_uint4(0, 0, 0, 0);
+			x[u] = rest ? __ldg(sh.grpPtr[j] + SIEVE_GROUP_U4 * g) : make_uint4(0, 0, 0, 0);
 			jp |= j << (4 * u);
 			rest &= rest - 1;
 		}
@@ -245,6 +289,7 @@ __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t b
 			else slow = true;
 		}
 	}
+#endif
 	if (slow) {
 		// compacted and resolved after the pass, with every lane busy (inline, one such block would stall the whole warp)
 		// (a full queue — a dynamic pass of a query with many lists — does not cost the pass: the block is resolved on the spot)
@@ -287,8 +332,8 @@ __device__ __forceinline__ void sieve_step(const SieveShared& sh, const uint32_t
 #pragma unroll 4
 	for (uint32_t j = 0; j < nS; ++j) {
 		const uint4* ptr = sh.sievePtr[j];
-		const uint4 x = onA ? __ldg(ptr + gA) : make_uint4(0, 0, 0, 0);      // { first posting, 3 x 32 block bits }
-		const uint4 y = onB ? __ldg(ptr + gB) : make_uint4(0, 0, 0, 0);
+		const uint4 x = onA ? __ldg(ptr + SIEVE_GROUP_U4 * gA) : make_uint4(0, 0, 0, 0);      // { first posting, 3 x 32 block bits }
+		const uint4 y = onB ? __ldg(ptr + SIEVE_GROUP_U4 * gB) : make_uint4(0, 0, 0, 0);
 #pragma unroll
 		for (int c = CREQ - 1; c >= 1; --c) {
 			ga[c] |= ga[c - 1] & x.y; gb[c] |= gb[c - 1] & x.z; gc[c] |= gc[c - 1] & x.w;
@@ -469,7 +514,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 		const float dens = fminf(1.0f, (float)d.total / ((float)nLists * (float)nBlocks));
 		if (tid < SV_MAXL) {
 			if ((uint32_t)tid < nLists) {
-				sh.grpPtr[tid] = ix.sieveGroups + (size_t)d.listSlot[tid] * NG;
+				sh.grpPtr[tid] = ix.sieveGroups + (size_t)d.listSlot[tid] * NG * SIEVE_GROUP_U4;
 				sh.listEnd[tid] = d.listOff[tid] + d.listLen[tid];
 				sh.mult[tid] = d.listMult[tid];
 			} else { sh.grpPtr[tid] = ix.sieveGroups; sh.listEnd[tid] = 0; sh.mult[tid] = 0; }
@@ -507,7 +552,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 			uint32_t sum = 0;
 			for (uint32_t i = 0; i < nLists; ++i)
 				for (uint32_t r = 0; r < d.listMult[i]; ++r) {
-					if (sum < SV_MAXL) sh.sievePtr[sum] = ix.sieveGroups + (size_t)d.listSlot[i] * NG;
+					if (sum < SV_MAXL) sh.sievePtr[sum] = ix.sieveGroups + (size_t)d.listSlot[i] * NG * SIEVE_GROUP_U4;
 					++sum;
 				}
 			sh.sumMult = sum;
