@@ -6,6 +6,8 @@ name=$1; shift
 mkdir -p build/variants build/vobj
 nvcc -std=c++17 -O3 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -gencode arch=compute_100a,code=sm_100a "$@" \
   -c stringsearchlib_b200/csrc/search.cu -o build/vobj/search_$name.o
-nvcc -shared -cudart static -o build/variants/$name.so build/obj/primitives.o build/obj/build.o build/obj/sieve.o build/vobj/search_$name.o \
+nvcc -std=c++17 -O3 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -gencode arch=compute_100a,code=sm_100a "$@" \
+  -c stringsearchlib_b200/csrc/sieve.cu -o build/vobj/sieve_$name.o
+nvcc -shared -cudart static -o build/variants/$name.so build/obj/primitives.o build/obj/build.o build/vobj/sieve_$name.o build/vobj/search_$name.o \
   build/obj/merge.o build/obj/digest.o build/obj/engine.o -gencode arch=compute_100a,code=sm_100a
 echo built build/variants/$name.so

@@ -150,15 +150,36 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 #endif
 #pragma unroll 4
 	for (uint32_t j = 0; j < nL; ++j) lm |= ((__ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + SIEVE_GROUP_U4 * g) + 1 + k) >> bit) & 1u) << j;
-	uint32_t ids[CAP], mus[CAP], m = 0;
+	unsigned long long ent[CAP];                             // (multiplicity, term id) of every posting inside the block
+	uint32_t m = 0;
 	SV_TICKS(5);
 	if (SV_TIMING && threadIdx.x == 0) sh.tim[8] += __popc(lm);
+#if SSB_SIEVE_INLINE
+	const uint32_t low = (1u << bit) - 1u;
+	const uint32_t my = k == 0 ? low : 0xFFFFFFFFu, mz = k == 1 ? low : (k > 1 ? 0xFFFFFFFFu : 0u), mw = k == 2 ? low : 0u;
+	const uint32_t bps = sieve_slot_bits(shift), nSlot = sieve_slots_per_group(shift);
+#endif
 	while (lm) {
 		const uint32_t j = (uint32_t)__ffs(lm) - 1u;
 		lm &= lm - 1;
-		uint32_t p;
-		sieve_locate(__ldg(sh.grpPtr[j] + SIEVE_GROUP_U4 * g), k, bit, p);
+		const uint4 x = __ldg(sh.grpPtr[j] + SIEVE_GROUP_U4 * g);
 		const uint32_t end = sh.listEnd[j], mu = sh.mult[j];
+#if SSB_SIEVE_INLINE
+		// a list with one posting in the block: its slot of the same sector says which term (no posting read)
+		const uint32_t r = __popc(x.y & my) + __popc(x.z & mz) + __popc(x.w & mw);
+		if (r < nSlot) {
+			const uint32_t* sp = reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + SIEVE_GROUP_U4 * g + 1);
+			const uint32_t wd = (r * bps) >> 5;
+			const uint32_t s0 = __ldg(sp + wd), s1 = wd < 3 ? __ldg(sp + wd + 1) : 0u;
+			const uint32_t v = __funnelshift_r(s0, s1, (r * bps) & 31u) & ((1u << bps) - 1u);
+			if (!(v >> shift)) {
+				if (m < CAP) ent[m++] = (((unsigned long long)mu) << 32) | ((blk << shift) | v); else sh.overflow = 2;
+				continue;
+			}
+		}
+#endif
+		uint32_t p;
+		sieve_locate(x, k, bit, p);
 		bool any = false, more = true;
 		while (more && p < end) {
 			uint32_t id[4];
@@ -169,7 +190,7 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 				const uint32_t b = id[t] >> shift;
 				if (id[t] == INF || b > blk) { more = false; break; }
 				if (b < blk) continue;                       // extra postings of lower blocks
-				if (m < CAP) { ids[m] = id[t]; mus[m] = mu; ++m; } else sh.overflow = 2;
+				if (m < CAP) ent[m++] = (((unsigned long long)mu) << 32) | id[t]; else sh.overflow = 2;
 				any = true;
 			}
 			p += 4;
@@ -177,12 +198,32 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 		if (!any) sh.overflow = 2;                           // bitmap and postings disagree: never trust, hand the query over
 	}
 	SV_TICKS(6);
-	for (uint32_t a = 0; a < m; ++a) {
-		uint32_t c = 0;
-		bool first = true;
-		for (uint32_t b = 0; b < m; ++b)
-			if (ids[b] == ids[a]) { if (b < a) first = false; c += mus[b]; }
-		if (first && c > cRej && (!onlyCount || c == onlyCount)) sieve_emit(sh, ids[a], c, tau);
+	// counts by comparing all pairs; the usual handful of entries is first copied to registers (independent loads of the
+	// local array instead of two dependent ones per pair)
+	if (m <= 8) {
+		uint32_t e[8], w[8];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const unsigned long long x = (uint32_t)i < m ? ent[i] : (unsigned long long)INF;
+			e[i] = (uint32_t)x; w[i] = (uint32_t)(x >> 32);
+		}
+#pragma unroll
+		for (int a2 = 0; a2 < 8; ++a2) {
+			uint32_t c = 0;
+			bool first = true;
+#pragma unroll
+			for (int b2 = 0; b2 < 8; ++b2)
+				if (e[b2] == e[a2]) { c += w[b2]; if (b2 < a2) first = false; }
+			if ((uint32_t)a2 < m && first && c > cRej && (!onlyCount || c == onlyCount)) sieve_emit(sh, e[a2], c, tau);
+		}
+	} else {
+		for (uint32_t a2 = 0; a2 < m; ++a2) {
+			uint32_t c = 0;
+			bool first = true;
+			for (uint32_t b2 = 0; b2 < m; ++b2)
+				if ((uint32_t)ent[b2] == (uint32_t)ent[a2]) { if (b2 < a2) first = false; c += (uint32_t)(ent[b2] >> 32); }
+			if (first && c > cRej && (!onlyCount || c == onlyCount)) sieve_emit(sh, (uint32_t)ent[a2], c, tau);
+		}
 	}
 	SV_TICKS(7);
 }
