@@ -648,12 +648,12 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	U* qn = reinterpret_cast<U*>(ws.qnorm.get());
 	// k_sieve_search pays a fixed price per query (set-up, pass plans, the general resolutions) and then grows slowly with the
 	// lists; the register merge of k_fast_search costs nothing up front and grows with every posting. Measured on B200 (batch
-	// 4096, ~9 lists per query): a tie at ~23 000 postings per query (a 5M-key index), k_sieve_search 10 % ahead at 46 000,
-	// 35 % behind at 6 000. The two kernels run one after the other, so the choice is made per batch, on the device, from the
+	// 4096, ~9 lists per query, 32-byte sieve groups): a tie at ~19 000 postings per query (a 4M-key index), k_sieve_search
+	// 3 % ahead at 23 000, 25 % at 46 000, 25 % behind at 11 500. The two kernels run one after the other, so the choice is made per batch, on the device, from the
 	// mean posting volume of its fast queries (k_sieve_search hands the whole batch over when it is below the mark; queries
 	// under a threshold count five-fold, see k_query_prep).
 	// ssb_set_search_path(1) sends every eligible query to k_sieve_search (the parity tests cover it on small indexes that way).
-	static const uint32_t sieveMinDefault = getenv("SSB_SIEVE_MIN_POSTINGS") ? (uint32_t)atoll(getenv("SSB_SIEVE_MIN_POSTINGS")) : 28000u;
+	static const uint32_t sieveMinDefault = getenv("SSB_SIEVE_MIN_POSTINGS") ? (uint32_t)atoll(getenv("SSB_SIEVE_MIN_POSTINGS")) : 20000u;
 	const uint32_t sieveMinTotal = g_search_path.load(std::memory_order_relaxed) == 1 ? 0u : sieveMinDefault;
 	k_query_prep<U><<<grid_for((size_t)nq * 32), 256, 0, s>>>(v, qc, ws.qoff.get(), nq, threshold, limit, qn, ws.desc.get(),
 	                                                          ws.fastList.get(), ws.denseList.get(), ws.counters.get(),
