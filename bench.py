@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--cpu-keys", type=int, default=1_000_000, help="vocabulary prefix indexed by the CPU reference leg")
     ap.add_argument("--cpu-queries", type=int, default=256, help="queries per step of the CPU reference leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-micro", action="store_true", help="skip the random-sector micro-benchmark behind roofline.random_access")
+    ap.add_argument("--no-micro", action="store_true", help="(kept for older scripts; no effect)")
     ap.add_argument("--profile-exchange", action="store_true", help="N>1: print CUDA-event times of the exchange phases (stderr)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2p-barrier", "nccl"],
                     help="N>1: p2p = export/merge kernels storing into NVLink peer memory with a device-side epoch hand-over, no "
@@ -462,23 +462,6 @@ def main():
                 traffic = json.load(f).get(("k_sieve_search" if last_st.get("nSieve", 0) * 2 > nb else "k_fast_search") + "_dram_bytes_per_launch")
         except (OSError, ValueError):
             traffic = None
-    # second denominator for k_sieve_search: its candidate-block reads are scattered 32-byte sector reads, and a B200 sustains far
-    # fewer of those per second than its copy bandwidth / 32 (scripts/micro/random_sectors.cu, measured live on this GPU at N=1)
-    random_access = None
-    probes = float(last_st.get("sieveProbes", 0))
-    micro = os.path.join(ROOT, "stringsearchlib_b200", "lib", "random_sectors")
-    if world == 1 and probes and os.path.exists(micro) and not args.no_micro:
-        try:
-            import subprocess
-            mj = json.loads(subprocess.run([micro, "--json"], capture_output=True, text=True, timeout=120, check=True).stdout.strip().splitlines()[-1])
-            rs_peak = float(mj["random_sector_reads_gsectors_per_s"]["footprint_1.1GB"])
-            rs_ach = probes / (k_ms / 1e3) / 1e9
-            random_access = {"what": "scattered posting reads of k_sieve_search (one 32-byte sector per candidate block and list) against the "
-                                     "GPU's measured rate of random sector reads out of HBM (footprint 1.1 GB; the index is 1.6 GB)",
-                             "sector_reads_per_launch": probes, "achieved": rs_ach, "peak": rs_peak, "unit": "Gsectors/s",
-                             "frac": rs_ach / rs_peak, "peak_3.2GB_footprint": float(mj["random_sector_reads_gsectors_per_s"]["footprint_3.2GB"])}
-        except Exception as e:
-            random_access = {"unavailable": str(e)[:200]}
     line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "wall_ms_per_step": 1e3 * float(np.mean(step_s)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic", "config": config, "clocks": clocks,
@@ -500,8 +483,11 @@ def main():
                             "device_only_keys_per_s": (hi - lo) / max((bms["total"] - bms["pack"]) / 1e3, 1e-9),
                             "terms": info["T"], "grams": info["G"], "postings": info["P"], "device_bytes": info["deviceBytes"]},
             "host_cores": cores}
-    if random_access:
-        line["roofline"]["random_access"] = random_access
+    if traffic:
+        # DRAM bytes the kernel really moves per launch (ncu capture of the same command, profiles/traffic.json) over the live kernel time:
+        # how busy HBM is, next to `frac`, which counts only the bytes the reference's algorithm needs
+        line["roofline"]["traffic_gbs"] = traffic / (k_ms / 1e3) / 1e9
+        line["roofline"]["traffic_frac"] = line["roofline"]["traffic_gbs"] / peak
     if global_sizes:
         line["index_build"]["global_sizes"] = global_sizes
     if exch_ms:

@@ -63,7 +63,7 @@ def build(force=False, verbose=False):
         if force or jobs or newer([srcp] + headers, out):
             run(["g++", "-std=c++17", "-O2", "-fPIC", "-fvisibility=hidden", "-shared", "-pthread", srcp, "-o", out,
                  "-L" + LIB, "-lssb_core", "-Wl,-rpath,$ORIGIN", "-lstdc++"])
-    # micro-benchmark behind bench.py's random-access figure (not part of the product)
+    # micro-benchmark behind DESIGN.md §5 (random sector reads out of HBM; not part of the product)
     micro = os.path.join(ROOT, "scripts", "micro", "random_sectors.cu")
     mout = os.path.join(LIB, "random_sectors")
     if force or newer([micro], mout):

@@ -90,7 +90,7 @@ int ssb_search_batch_device(ssb_index* ix, const void* const* queries, uint32_t 
  * ms[0] = whole device part, ms[1] = k_sieve_search + k_fast_search alone (CUDA events on the engine's stream).
  * stats[]: 0 nFast 1 nDense 2 nOverflow 3 postings touched by fast queries 4 answered by k_sieve_search
  *          5 handed from k_sieve_search to k_fast_search 6 of those, given up mid-query
- *          7 (candidate block, list) pairs k_sieve_search resolved = scattered posting reads */
+ *          7 (candidate block, list) pairs k_sieve_search resolved */
 int ssb_search_resident(ssb_index* ix, uint32_t nq, float threshold, uint32_t limit, float ms[2], uint64_t stats[8]);
 
 /* ---- multi-GPU (key-range shards, one process per GPU): fixed-size per-query records for an all-gather ----

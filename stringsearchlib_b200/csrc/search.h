@@ -37,7 +37,7 @@ struct SearchStats {
 	uint32_t nSieve = 0, nSieveHandover = 0, nSieveGiveUp = 0;   // k_sieve_search: answered / handed to k_fast_search / of those, given up mid-query
 	uint64_t postingsTouched = 0;   // sum over fast queries of posting-list lengths (algorithmic bytes / 4)
 	uint64_t candidates = 0;
-	uint64_t sieveProbes = 0;       // k_sieve_search: (candidate block, list) pairs resolved = scattered posting reads out of HBM
+	uint64_t sieveProbes = 0;       // k_sieve_search: (candidate block, list) pairs resolved
 	float msDevice = 0;             // CUDA-event time of the device part of the last batch
 	float msFastKernel = 0;         // CUDA-event time of k_fast_search alone
 };
