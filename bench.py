@@ -456,7 +456,8 @@ def main():
     achieved = algo_bytes / (k_ms / 1e3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    # (the ncu capture is of the default single-GPU workload: other sizes / shard counts have no traffic figure)
+    if os.path.exists(tp) and world == 1 and args.keys == 10_000_000 and args.batch == 4096 and args.limit == 100 and args.threshold == 0.0:
         try:
             with open(tp) as f:
                 traffic = json.load(f).get(("k_sieve_search" if last_st.get("nSieve", 0) * 2 > nb else "k_fast_search") + "_dram_bytes_per_launch")
