@@ -17,14 +17,12 @@ namespace ssb {
 
 constexpr int MAX_GSIZE = 8;
 constexpr uint32_t SIEVE_GROUP_BLOCKS = 96;   // blocks per sieve group (sieve.cu)
-// SSB_SIEVE_INLINE=1 (default): a group is 32 bytes — { first, 3 x 32 block bits } + 128 bits of SLOTS: for the group's r-th occupied
-// block, (shift + 1) bits at position r * (shift + 1): the offset of the list's first posting inside the block and a flag
-// "the block holds more postings of the list". Block number + offset IS the term id, so k_sieve_search resolves a candidate
-// block from the sector it has just streamed instead of a scattered read of the posting list. 0: 16-byte groups, postings read.
-#ifndef SSB_SIEVE_INLINE
-#define SSB_SIEVE_INLINE 1
-#endif
-constexpr uint32_t SIEVE_GROUP_U4 = SSB_SIEVE_INLINE ? 2 : 1;      // 16-byte units per group
+// Two layouts of the same bitmaps (sieve.cu): 16-byte groups { first, 3 x 32 block bits } and, on indexes of up to
+// SIEVE_INLINE_MAX_TERMS terms, 32-byte groups that add 128 bits of SLOTS: for the group's r-th occupied block, (shift + 1) bits
+// at position r * (shift + 1): the offset of the list's first posting inside the block and a flag "the block holds more postings
+// of the list". Block number + offset IS the term id, so k_sieve_search<.., true> resolves a candidate block from the sector it
+// has just streamed instead of a scattered read of the posting list — at twice the stream. Which one a batch uses: search.cu.
+constexpr uint32_t SIEVE_INLINE_MAX_TERMS = 32u << 20;
 __host__ __device__ inline uint32_t sieve_slot_bits(int shift) { return (uint32_t)shift + 1u; }
 __host__ __device__ inline uint32_t sieve_slots_per_group(int shift) { const uint32_t n = 126u / sieve_slot_bits(shift); return n < SIEVE_GROUP_BLOCKS ? n : SIEVE_GROUP_BLOCKS; }
 
@@ -84,14 +82,15 @@ struct DeviceIndex {
 	uint32_t sieveNGroups = 0;   // 96-block groups per bitmap; 0 = the index has no sieve
 	uint32_t sieveSlots = 0;     // grams that have a bitmap
 	DevBuf<uint32_t> sieveSlot;  // [G] bitmap slot of the gram, 0xFFFFFFFF = none (short list)
-	DevBuf<uint32_t> sieveGroups;// [sieveSlots * sieveNGroups * 4 * SIEVE_GROUP_U4] per group { first posting index, 3 x 32 block bits } (+ 128 bits of slots)
+	DevBuf<uint32_t> sieveGroups;// [sieveSlots * sieveNGroups * 4] per group { first posting index, 3 x 32 block bits }
+	DevBuf<uint32_t> sieveInline;// [sieveSlots * sieveNGroups * 8] the same + 128 bits of slots per group; empty on large indexes
 
 	size_t device_bytes() const
 	{
 		return symTable.bytes() + validLut.bytes() + gramCodes.bytes() + gramOff.bytes() + postings.bytes() + termOff.bytes() +
 		       termChars.bytes() + termEdgeOff.bytes() + edgeKid.bytes() + edgeW.bytes() + shortTerms.bytes() + keyOff.bytes() +
 		       keyChars.bytes() + keyEdgeOff.bytes() + keyEdgeTerm.bytes() + keyEdgeW.bytes() + keyWmax.bytes() + keyRow.bytes() +
-		       keyHash.bytes() + sieveSlot.bytes() + sieveGroups.bytes();
+		       keyHash.bytes() + sieveSlot.bytes() + sieveGroups.bytes() + sieveInline.bytes();
 	}
 };
 

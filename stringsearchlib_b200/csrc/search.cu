@@ -61,7 +61,8 @@ struct IndexView {
 	int sieveShift;
 	uint32_t sieveNGroups;
 	const uint32_t* sieveSlot;
-	const uint4* sieveGroups;
+	const uint4* sieveGroups;                               // 16-byte groups
+	const uint4* sieveInline;                               // 32-byte groups (nullptr: not built for this index)
 };
 
 IndexView make_view(const DeviceIndex& ix)
@@ -81,6 +82,7 @@ IndexView make_view(const DeviceIndex& ix)
 	v.keyWmax = ix.keyWmax.get(); v.keyRow = ix.keyRow.get();
 	v.sieveShift = ix.sieveShift; v.sieveNGroups = ix.sieveSlots ? ix.sieveNGroups : 0u;
 	v.sieveSlot = ix.sieveSlot.get(); v.sieveGroups = reinterpret_cast<const uint4*>(ix.sieveGroups.get());
+	v.sieveInline = reinterpret_cast<const uint4*>(ix.sieveInline.get());
 	return v;
 }
 
@@ -609,8 +611,10 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
 		SSB_CUDA(cudaFuncSetAttribute(k_fast_search<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
 		const int maxSv = (int)(((sizeof(SieveShared) + 15) & ~size_t(15)) + (size_t)FS_BUF_MAX * 8 + (size_t)FS_DEF_EXT * 8);
-		SSB_CUDA(cudaFuncSetAttribute(k_sieve_search<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSv));
-		SSB_CUDA(cudaFuncSetAttribute(k_sieve_search<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSv));
+		SSB_CUDA(cudaFuncSetAttribute(k_sieve_search<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSv));
+		SSB_CUDA(cudaFuncSetAttribute(k_sieve_search<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSv));
+		SSB_CUDA(cudaFuncSetAttribute(k_sieve_search<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSv));
+		SSB_CUDA(cudaFuncSetAttribute(k_sieve_search<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSv));
 		SSB_CUDA(cudaFuncSetAttribute(k_order_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ORDER_MAX * 8)));
 		lc.numSMs = n;
 	});
@@ -630,7 +634,7 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 		const int scfg = bufIdx + (defExt ? 3 : 0);
 		if (!lc.sieveCtas[scfg]) {
 			int c = 0;
-			SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_sieve_search<U>, SV_THREADS, svBytes));
+			SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_sieve_search<U, true>, SV_THREADS, svBytes));      // (both layouts: same bounds)
 			lc.sieveCtas[scfg] = std::max(c, 1);
 			if (getenv("SSB_DEBUG"))
 				fprintf(stderr, "[ssb] k_sieve_search: sizeof(SieveShared)=%zu, dynamic smem=%zu B, %d CTAs/SM x %d threads\n", sizeof(SieveShared),
@@ -680,9 +684,20 @@ void run_device(const DeviceIndex& ix, SearchWorkspace& ws, uint32_t nq, float t
 	if (direct) { ho.kids = hr->kids; ho.scores = hr->scores; ho.rows = hr->rows; ho.strs = reinterpret_cast<uint64_t*>(hr->strs); ho.strBase = hr->strBase; }
 	if (useSieve) {
 		const unsigned sgrid = (unsigned)std::min<size_t>((size_t)numSMs * sieveCtasPerSM, std::max<uint32_t>(nq, 1));
-		k_sieve_search<U><<<sgrid, SV_THREADS, svBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(), ws.fastList2.get(),
-		                                                    limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(),
-		                                                    statCounters, bufCap, threshold, defExt, sieveMinTotal, ho);
+		// which layout of the bitmaps the batch streams (index.h): the 32-byte groups resolve a candidate block without touching
+		// the postings but stream twice the bytes — they pay where candidate blocks are dense, i.e. while a query without (much
+		// of) a threshold still looks for its k two-match terms: 10M keys, batch 4096, top-100 at threshold 0 / 0.3 / 0.5 (top-500):
+		// 0.69 / 0.58 / 0.47 ms against 0.72 / 0.61 / 0.36 ms with the 16-byte groups
+		static const float inlineMaxThreshold = getenv("SSB_SIEVE_INLINE_MAX_THRESHOLD") ? (float)atof(getenv("SSB_SIEVE_INLINE_MAX_THRESHOLD")) : 0.3f;
+		const bool inl = v.sieveInline != nullptr && !(threshold > inlineMaxThreshold);
+		if (inl)
+			k_sieve_search<U, true><<<sgrid, SV_THREADS, svBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(), ws.fastList2.get(),
+			                                                          limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(),
+			                                                          statCounters, bufCap, threshold, defExt, sieveMinTotal, ho);
+		else
+			k_sieve_search<U, false><<<sgrid, SV_THREADS, svBytes, s>>>(v, ws.desc.get(), qn, ws.fastList.get(), ws.counters.get(), ws.fastList2.get(),
+			                                                           limit, stride, ws.outCount.get(), ws.outKid.get(), ws.outScore.get(),
+			                                                           statCounters, bufCap, threshold, defExt, sieveMinTotal, ho);
 		SSB_LAUNCH_CHECK();
 	}
 	const uint32_t* fl = useSieve ? ws.fastList2.get() : ws.fastList.get();

@@ -127,9 +127,11 @@ __device__ __forceinline__ bool sieve_locate(const uint4 x, uint32_t k, uint32_t
 
 // general resolution of one block (more than SV_PU lists hit it, or a list has several postings in or just below it):
 // local arrays, counts by comparing all pairs. Rare, and run for a compacted list of such blocks after the pass.
+template <bool INL>
 __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_t onlyCount, unsigned long long tau)
 {
 	constexpr int CAP = 48;
+	constexpr uint32_t GU = INL ? 2 : 1;                     // 16-byte units per group
 	const int shift = sh.ix.sieveShift;
 	const uint32_t* __restrict__ postings = sh.ix.postings;
 	const uint32_t v = blk >> 5, g = v / 3u, k = v - 3u * g, bit = blk & 31u;
@@ -149,26 +151,23 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 #define SV_TICKS(slot) do { } while (0)
 #endif
 #pragma unroll 4
-	for (uint32_t j = 0; j < nL; ++j) lm |= ((__ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + SIEVE_GROUP_U4 * g) + 1 + k) >> bit) & 1u) << j;
+	for (uint32_t j = 0; j < nL; ++j) lm |= ((__ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + GU * g) + 1 + k) >> bit) & 1u) << j;
 	unsigned long long ent[CAP];                             // (multiplicity, term id) of every posting inside the block
 	uint32_t m = 0;
 	SV_TICKS(5);
 	if (SV_TIMING && threadIdx.x == 0) sh.tim[8] += __popc(lm);
-#if SSB_SIEVE_INLINE
 	const uint32_t low = (1u << bit) - 1u;
 	const uint32_t my = k == 0 ? low : 0xFFFFFFFFu, mz = k == 1 ? low : (k > 1 ? 0xFFFFFFFFu : 0u), mw = k == 2 ? low : 0u;
 	const uint32_t bps = sieve_slot_bits(shift), nSlot = sieve_slots_per_group(shift);
-#endif
 	while (lm) {
 		const uint32_t j = (uint32_t)__ffs(lm) - 1u;
 		lm &= lm - 1;
-		const uint4 x = __ldg(sh.grpPtr[j] + SIEVE_GROUP_U4 * g);
+		const uint4 x = __ldg(sh.grpPtr[j] + GU * g);
 		const uint32_t end = sh.listEnd[j], mu = sh.mult[j];
-#if SSB_SIEVE_INLINE
 		// a list with one posting in the block: its slot of the same sector says which term (no posting read)
 		const uint32_t r = __popc(x.y & my) + __popc(x.z & mz) + __popc(x.w & mw);
-		if (r < nSlot) {
-			const uint32_t* sp = reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + SIEVE_GROUP_U4 * g + 1);
+		if (INL && r < nSlot) {
+			const uint32_t* sp = reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + GU * g + 1);
 			const uint32_t wd = (r * bps) >> 5;
 			const uint32_t s0 = __ldg(sp + wd), s1 = wd < 3 ? __ldg(sp + wd + 1) : 0u;
 			const uint32_t v = __funnelshift_r(s0, s1, (r * bps) & 31u) & ((1u << bps) - 1u);
@@ -177,7 +176,6 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 				continue;
 			}
 		}
-#endif
 		uint32_t p;
 		sieve_locate(x, k, bit, p);
 		bool any = false, more = true;
@@ -231,8 +229,10 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 // ---- RESOLVE one block that passed the sieve (one thread per block, a full warp of blocks at a time). Returns the number
 // of lists that hit it. onlyCount != 0: emit only terms with exactly that many matches (second phase: the others are in the
 // buffer already).
+template <bool INL>
 __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t blk, const uint32_t onlyCount, const unsigned long long tau)
 {
+	constexpr uint32_t GU = INL ? 2 : 1;
 	const int shift = sh.ix.sieveShift;
 	const uint32_t* __restrict__ postings = sh.ix.postings;
 	const uint32_t nL = sh.nLists;
@@ -245,97 +245,96 @@ __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t b
 		uint32_t wv[SV_MAXL];
 #pragma unroll
 		for (int j = 0; j < SV_MAXL; ++j)
-			wv[j] = (uint32_t)j < nL ? __ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + SIEVE_GROUP_U4 * g) + 1 + k) : 0u;
+			wv[j] = (uint32_t)j < nL ? __ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + GU * g) + 1 + k) : 0u;
 #pragma unroll
 		for (int j = 0; j < SV_MAXL; ++j) lm |= ((wv[j] >> bit) & 1u) << j;
 	}
 	const uint32_t ns = __popc(lm);
 	const uint32_t low = (1u << bit) - 1u;
 	const uint32_t my = k == 0 ? low : 0xFFFFFFFFu, mz = k == 1 ? low : (k > 1 ? 0xFFFFFFFFu : 0u), mw = k == 2 ? low : 0u;
-#if SSB_SIEVE_INLINE
-	// (2) the group of the first SV_PU lists that hit: the block's rank among the group's occupied blocks, then (3) that slot of
-	// the same 32-byte sector (it has just arrived): the offset of the list's posting inside the block — block number + offset is
-	// the term id, no posting is read. A block in which the list has several postings, or whose slot did not fit, is left to
-	// the general resolution.
 	bool slow = ns > SV_PU;
-	uint32_t h[SV_PU], mu[SV_PU], rk[SV_PU], jp = 0;
-	const uint32_t bps = sieve_slot_bits(shift), nSlot = sieve_slots_per_group(shift);
-	{
-		uint4 x[SV_PU];
-		uint32_t rest = lm;
-#pragma unroll
-		for (int u = 0; u < SV_PU; ++u) {
-			const uint32_t j = rest ? (uint32_t)__ffs(rest) - 1u : 0u;
-			x[u] = rest ? __ldg(sh.grpPtr[j] + SIEVE_GROUP_U4 * g) : make_uint4(0, 0, 0, 0);
-			jp |= j << (4 * u);
-			rest &= rest - 1;
+	uint32_t h[SV_PU], mu[SV_PU];
+	if constexpr (INL) {
+		// (2) the group of the first SV_PU lists that hit: the block's rank among the group's occupied blocks, then (3) that slot of
+		// the same 32-byte sector (it has just arrived): the offset of the list's posting inside the block — block number + offset is
+		// the term id, no posting is read. A block in which the list has several postings, or whose slot did not fit, is left to
+		// the general resolution.
+		uint32_t rk[SV_PU], jp = 0;
+		const uint32_t bps = sieve_slot_bits(shift), nSlot = sieve_slots_per_group(shift);
+		{
+			uint4 x[SV_PU];
+			uint32_t rest = lm;
+	#pragma unroll
+			for (int u = 0; u < SV_PU; ++u) {
+				const uint32_t j = rest ? (uint32_t)__ffs(rest) - 1u : 0u;
+				x[u] = rest ? __ldg(sh.grpPtr[j] + GU * g) : make_uint4(0, 0, 0, 0);
+				jp |= j << (4 * u);
+				rest &= rest - 1;
+			}
+	#pragma unroll
+			for (int u = 0; u < SV_PU; ++u) rk[u] = __popc(x[u].y & my) + __popc(x[u].z & mz) + __popc(x[u].w & mw);
 		}
-#pragma unroll
-		for (int u = 0; u < SV_PU; ++u) rk[u] = __popc(x[u].y & my) + __popc(x[u].z & mz) + __popc(x[u].w & mw);
-	}
-	{
-		uint32_t s0[SV_PU], s1[SV_PU];
-#pragma unroll
+		{
+			uint32_t s0[SV_PU], s1[SV_PU];
+	#pragma unroll
+			for (int u = 0; u < SV_PU; ++u) {
+				const uint32_t j = (jp >> (4 * u)) & 15u;
+				const bool on = (uint32_t)u < ns && rk[u] < nSlot;
+				const uint32_t wd = (rk[u] * bps) >> 5;
+				const uint32_t* sp = reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + GU * g + 1);
+				s0[u] = on ? __ldg(sp + wd) : 0u;
+				s1[u] = on && wd < 3 ? __ldg(sp + wd + 1) : 0u;
+				mu[u] = sh.mult[j];
+			}
+	#pragma unroll
+			for (int u = 0; u < SV_PU; ++u) {
+				const uint32_t v = __funnelshift_r(s0[u], s1[u], (rk[u] * bps) & 31u) & ((1u << bps) - 1u);
+				h[u] = INF;
+				if ((uint32_t)u < ns) {
+					if (rk[u] < nSlot && !(v >> shift)) h[u] = (blk << shift) | v;
+					else slow = true;
+				}
+			}
+		}
+	} else {
+		uint32_t idx[SV_PU], jp = 0;
+		{
+			uint4 x[SV_PU];
+			uint32_t rest = lm;
+	#pragma unroll
+			for (int u = 0; u < SV_PU; ++u) {
+				const uint32_t j = rest ? (uint32_t)__ffs(rest) - 1u : 0u;
+				x[u] = rest ? __ldg(sh.grpPtr[j] + GU * g) : make_uint4(0, 0, 0, 0);
+				jp |= j << (4 * u);
+				rest &= rest - 1;
+			}
+	#pragma unroll
+			for (int u = 0; u < SV_PU; ++u) idx[u] = x[u].x + __popc(x[u].y & my) + __popc(x[u].z & mz) + __popc(x[u].w & mw);
+		}
+		// Three postings per list decide the two common cases: the first one is the block's only posting of the list, or one
+		// extra posting of a lower block precedes it.
+	#pragma unroll
 		for (int u = 0; u < SV_PU; ++u) {
 			const uint32_t j = (jp >> (4 * u)) & 15u;
-			const bool on = (uint32_t)u < ns && rk[u] < nSlot;
-			const uint32_t wd = (rk[u] * bps) >> 5;
-			const uint32_t* sp = reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + SIEVE_GROUP_U4 * g + 1);
-			s0[u] = on ? __ldg(sp + wd) : 0u;
-			s1[u] = on && wd < 3 ? __ldg(sp + wd + 1) : 0u;
+			const uint32_t end = (uint32_t)u < ns ? sh.listEnd[j] : 0u;
 			mu[u] = sh.mult[j];
-		}
-#pragma unroll
-		for (int u = 0; u < SV_PU; ++u) {
-			const uint32_t v = __funnelshift_r(s0[u], s1[u], (rk[u] * bps) & 31u) & ((1u << bps) - 1u);
+			const uint32_t id0 = idx[u] < end ? __ldg(postings + idx[u]) : INF;
+			const uint32_t id1 = idx[u] + 1 < end ? __ldg(postings + idx[u] + 1) : INF;
+			const uint32_t id2 = idx[u] + 2 < end ? __ldg(postings + idx[u] + 2) : INF;
+			const uint32_t b0 = id0 >> shift, b1 = id1 >> shift, b2 = id2 >> shift;
 			h[u] = INF;
 			if ((uint32_t)u < ns) {
-				if (rk[u] < nSlot && !(v >> shift)) h[u] = (blk << shift) | v;
+				if (b0 == blk && (id1 == INF || b1 != blk)) h[u] = id0;
+				else if (id0 != INF && b0 < blk && id1 != INF && b1 == blk && (id2 == INF || b2 != blk)) h[u] = id1;
 				else slow = true;
 			}
 		}
 	}
-#else
-	uint32_t idx[SV_PU], jp = 0;
-	{
-		uint4 x[SV_PU];
-		uint32_t rest = lm;
-#pragma unroll
-		for (int u = 0; u < SV_PU; ++u) {
-			const uint32_t j = rest ? (uint32_t)__ffs(rest) - 1u : 0u;
-			x[u] = rest ? __ldg(sh.grpPtr[j] + SIEVE_GROUP_U4 * g) : make_uint4(0, 0, 0, 0);
-			jp |= j << (4 * u);
-			rest &= rest - 1;
-		}
-#pragma unroll
-		for (int u = 0; u < SV_PU; ++u) idx[u] = x[u].x + __popc(x[u].y & my) + __popc(x[u].z & mz) + __popc(x[u].w & mw);
-	}
-	bool slow = ns > SV_PU;
-	uint32_t h[SV_PU], mu[SV_PU];
-	// Three postings per list decide the two common cases: the first one is the block's only posting of the list, or one
-	// extra posting of a lower block precedes it.
-#pragma unroll
-	for (int u = 0; u < SV_PU; ++u) {
-		const uint32_t j = (jp >> (4 * u)) & 15u;
-		const uint32_t end = (uint32_t)u < ns ? sh.listEnd[j] : 0u;
-		mu[u] = sh.mult[j];
-		const uint32_t id0 = idx[u] < end ? __ldg(postings + idx[u]) : INF;
-		const uint32_t id1 = idx[u] + 1 < end ? __ldg(postings + idx[u] + 1) : INF;
-		const uint32_t id2 = idx[u] + 2 < end ? __ldg(postings + idx[u] + 2) : INF;
-		const uint32_t b0 = id0 >> shift, b1 = id1 >> shift, b2 = id2 >> shift;
-		h[u] = INF;
-		if ((uint32_t)u < ns) {
-			if (b0 == blk && (id1 == INF || b1 != blk)) h[u] = id0;
-			else if (id0 != INF && b0 < blk && id1 != INF && b1 == blk && (id2 == INF || b2 != blk)) h[u] = id1;
-			else slow = true;
-		}
-	}
-#endif
 	if (slow) {
 		// compacted and resolved after the pass, with every lane busy (inline, one such block would stall the whole warp)
 		// (a full queue — a dynamic pass of a query with many lists — does not cost the pass: the block is resolved on the spot)
 		const uint32_t si = atomicAdd(&sh.nSlow, 1u);
-		if (si < SV_SLOWCAP) sh.slowQ[si] = blk; else resolve_slow(sh, blk, onlyCount, tau);
+		if (si < SV_SLOWCAP) sh.slowQ[si] = blk; else resolve_slow<INL>(sh, blk, onlyCount, tau);
 		return ns;
 	}
 	// integer pre-filter refined by the block's first id (identity mode: kid == term id >= first id of the block)
@@ -363,9 +362,10 @@ __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t b
 // needs again are still in L1, without a CTA-wide barrier, and while the other warps keep streaming.
 // one bitmap step of a warp: lane l streams groups gA and gB of every counted list through the bit-sliced threshold counter;
 // m = the blocks that at least CREQ lists hit (3 words of group A, 3 of group B)
-template <int CREQ>
+template <int CREQ, bool INL>
 __device__ __forceinline__ void sieve_step(const SieveShared& sh, const uint32_t nS, const uint32_t gA, const uint32_t gB, const uint32_t g1, uint32_t (&m)[6])
 {
+	constexpr uint32_t GU = INL ? 2 : 1;
 	uint32_t ga[CREQ], gb[CREQ], gc[CREQ], ha[CREQ], hb[CREQ], hc[CREQ];
 #pragma unroll
 	for (int c = 0; c < CREQ; ++c) { ga[c] = 0; gb[c] = 0; gc[c] = 0; ha[c] = 0; hb[c] = 0; hc[c] = 0; }
@@ -373,8 +373,8 @@ __device__ __forceinline__ void sieve_step(const SieveShared& sh, const uint32_t
 #pragma unroll 4
 	for (uint32_t j = 0; j < nS; ++j) {
 		const uint4* ptr = sh.sievePtr[j];
-		const uint4 x = onA ? __ldg(ptr + SIEVE_GROUP_U4 * gA) : make_uint4(0, 0, 0, 0);      // { first posting, 3 x 32 block bits }
-		const uint4 y = onB ? __ldg(ptr + SIEVE_GROUP_U4 * gB) : make_uint4(0, 0, 0, 0);
+		const uint4 x = onA ? __ldg(ptr + GU * gA) : make_uint4(0, 0, 0, 0);      // { first posting, 3 x 32 block bits }
+		const uint4 y = onB ? __ldg(ptr + GU * gB) : make_uint4(0, 0, 0, 0);
 #pragma unroll
 		for (int c = CREQ - 1; c >= 1; --c) {
 			ga[c] |= ga[c - 1] & x.y; gb[c] |= gb[c - 1] & x.z; gc[c] |= gc[c - 1] & x.w;
@@ -390,7 +390,7 @@ __device__ __forceinline__ void sieve_step(const SieveShared& sh, const uint32_t
 // brings the number of terms with two or more matches to k (sieve_emit) turns maxPos into the bound — k such terms lie below
 // it — and every chunk that starts at or behind it is sieved for three. One pass, and the two-list stretch is exactly as long
 // as the data needs (a planned pass is either too long: candidate blocks for nothing, or too short: another pass).
-template <int CREQ, bool DYN>
+template <int CREQ, bool DYN, bool INL>
 __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, const uint32_t g1, const uint32_t nS, const uint32_t onlyCount)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -410,9 +410,9 @@ __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, co
 		if (DYN) {
 			if (lane == 0) atomicMax(&sh.maxPos, min(base + 64, g1));
 			__syncwarp();
-			if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp)) sieve_step<3>(sh, nS, gA, gB, g1, m);
-			else sieve_step<2>(sh, nS, gA, gB, g1, m);
-		} else sieve_step<CREQ>(sh, nS, gA, gB, g1, m);
+			if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp)) sieve_step<3, INL>(sh, nS, gA, gB, g1, m);
+			else sieve_step<2, INL>(sh, nS, gA, gB, g1, m);
+		} else sieve_step<CREQ, INL>(sh, nS, gA, gB, g1, m);
 		uint32_t left = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]) + __popc(m[5]);
 		SV_TICKW(0);
 		// rounds: every lane pushes up to `quota` of its blocks, then the queue is drained down to less than a warp's worth.
@@ -449,7 +449,7 @@ __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, co
 				const uint32_t blk = wq[qn + lane];
 				__syncwarp();
 				if (DYN) tau = *reinterpret_cast<volatile unsigned long long*>(&sh.tau);      // (it tightens while the pass runs)
-				np += resolve_block(sh, blk, onlyCount, tau);
+				np += resolve_block<INL>(sh, blk, onlyCount, tau);
 			}
 			SV_TICKW(2);
 		}
@@ -457,23 +457,24 @@ __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, co
 	if (qn) {
 		const uint32_t blk = (uint32_t)lane < qn ? wq[lane] : INF;
 		if (DYN) tau = *reinterpret_cast<volatile unsigned long long*>(&sh.tau);
-		if (blk != INF) np += resolve_block(sh, blk, onlyCount, tau);
+		if (blk != INF) np += resolve_block<INL>(sh, blk, onlyCount, tau);
 	}
 #pragma unroll
 	for (int o = 16; o; o >>= 1) { nc += __shfl_xor_sync(0xffffffffu, nc, o); np += __shfl_xor_sync(0xffffffffu, np, o); }
 	if (lane == 0) { atomicAdd(&sh.nCand, nc); atomicAdd(&sh.nProbe, np); }
 }
 
+template <bool INL>
 __device__ __forceinline__ void sieve_dispatch(SieveShared& sh, uint32_t creq, uint32_t g0, uint32_t g1, uint32_t nS, uint32_t onlyCount)
 {
 	// thresholds without an instantiation of their own use the next lower one: a superset of the blocks, RESOLVE counts exactly
-	if (sh.dyn) sieve_groups<2, true>(sh, g0, g1, nS, onlyCount);
-	else if (creq <= 1) sieve_groups<1, false>(sh, g0, g1, nS, onlyCount);
-	else if (creq == 2) sieve_groups<2, false>(sh, g0, g1, nS, onlyCount);
-	else if (creq == 3) sieve_groups<3, false>(sh, g0, g1, nS, onlyCount);
-	else if (creq < 6) sieve_groups<4, false>(sh, g0, g1, nS, onlyCount);
-	else if (creq < 8) sieve_groups<6, false>(sh, g0, g1, nS, onlyCount);
-	else sieve_groups<8, false>(sh, g0, g1, nS, onlyCount);
+	if (sh.dyn) sieve_groups<2, true, INL>(sh, g0, g1, nS, onlyCount);
+	else if (creq <= 1) sieve_groups<1, false, INL>(sh, g0, g1, nS, onlyCount);
+	else if (creq == 2) sieve_groups<2, false, INL>(sh, g0, g1, nS, onlyCount);
+	else if (creq == 3) sieve_groups<3, false, INL>(sh, g0, g1, nS, onlyCount);
+	else if (creq < 6) sieve_groups<4, false, INL>(sh, g0, g1, nS, onlyCount);
+	else if (creq < 8) sieve_groups<6, false, INL>(sh, g0, g1, nS, onlyCount);
+	else sieve_groups<8, false, INL>(sh, g0, g1, nS, onlyCount);
 }
 
 // expected candidate blocks per bitmap word when a block needs >= c of K lists, every list setting a block with probability p
@@ -489,7 +490,7 @@ __device__ float sieve_rate(uint32_t K, uint32_t c, float p)
 	return 32.0f * e;
 }
 
-template <class U>
+template <class U, bool INL>
 __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexView ix, const QDesc* __restrict__ desc, const U* __restrict__ qnorm,
                                                              const uint32_t* __restrict__ fastList, uint32_t* __restrict__ counters,
                                                              uint32_t* __restrict__ handList, uint32_t limit, uint32_t outStride,
@@ -509,6 +510,8 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 	}
 	const uint32_t k = limit;
 	const uint32_t NG = ix.sieveNGroups;
+	constexpr uint32_t GU = INL ? 2 : 1;                                   // 16-byte units per group
+	const uint4* const sieveBase = INL ? ix.sieveInline : ix.sieveGroups;
 	const int shift = ix.sieveShift;
 	const uint32_t nBlocks = (uint32_t)((((unsigned long long)ix.T - 1) >> shift) + 1);
 	if (tid == 0) {
@@ -555,10 +558,10 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 		const float dens = fminf(1.0f, (float)d.total / ((float)nLists * (float)nBlocks));
 		if (tid < SV_MAXL) {
 			if ((uint32_t)tid < nLists) {
-				sh.grpPtr[tid] = ix.sieveGroups + (size_t)d.listSlot[tid] * NG * SIEVE_GROUP_U4;
+				sh.grpPtr[tid] = sieveBase + (size_t)d.listSlot[tid] * NG * GU;
 				sh.listEnd[tid] = d.listOff[tid] + d.listLen[tid];
 				sh.mult[tid] = d.listMult[tid];
-			} else { sh.grpPtr[tid] = ix.sieveGroups; sh.listEnd[tid] = 0; sh.mult[tid] = 0; }
+			} else { sh.grpPtr[tid] = sieveBase; sh.listEnd[tid] = 0; sh.mult[tid] = 0; }
 		} else if (tid >= 32 && tid < 32 + 9) {
 			const uint32_t c = tid - 32;
 			sh.rateTab[c] = fmaxf(3.0f * sieve_rate(nLists, max(c, 1u), dens), 1e-4f);      // per 96-block group
@@ -593,7 +596,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 			uint32_t sum = 0;
 			for (uint32_t i = 0; i < nLists; ++i)
 				for (uint32_t r = 0; r < d.listMult[i]; ++r) {
-					if (sum < SV_MAXL) sh.sievePtr[sum] = ix.sieveGroups + (size_t)d.listSlot[i] * NG * SIEVE_GROUP_U4;
+					if (sum < SV_MAXL) sh.sievePtr[sum] = sieveBase + (size_t)d.listSlot[i] * NG * GU;
 					++sum;
 				}
 			sh.sumMult = sum;
@@ -621,7 +624,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 			if (tid == 0) { sh.defCount = 0; sh.cRej = sh.cmin ? sh.cmin - 1 : 0; }
 			__syncthreads();
 			SV_TICK(3);
-			for (uint32_t i = tid; i < n; i += SV_THREADS) resolve_slow(sh, sh.slowQ[i], onlyCount, sh.tau);
+			for (uint32_t i = tid; i < n; i += SV_THREADS) resolve_slow<INL>(sh, sh.slowQ[i], onlyCount, sh.tau);
 			SV_TICK(6);
 			__syncthreads();
 			SV_TICK(7);
@@ -724,7 +727,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 				const uint32_t slowSnap = sh.nSlow;                // (lazy mode) entries of earlier passes
 				if (tid == 0) atomicAdd(&counters[24], 1u);
 				// ---- sieve + resolve, then the blocks left to the general resolution, then what was deferred
-				sieve_dispatch(sh, creq, w0, w1, nSieve, onlyCount);
+				sieve_dispatch<INL>(sh, creq, w0, w1, nSieve, onlyCount);
 				__syncthreads();
 				SV_TICK(2);
 				const uint32_t nCand = sh.nCand;
@@ -733,7 +736,7 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 				{
 					if (!lazySlow) {
 						const uint32_t nSlow = min(sh.nSlow, (uint32_t)SV_SLOWCAP);
-						for (uint32_t i = tid; i < nSlow; i += SV_THREADS) resolve_slow(sh, sh.slowQ[i], onlyCount, sh.tau);
+						for (uint32_t i = tid; i < nSlow; i += SV_THREADS) resolve_slow<INL>(sh, sh.slowQ[i], onlyCount, sh.tau);
 						if (nSlow) __syncthreads();
 					}
 					if (sh.overflow == 0) {
