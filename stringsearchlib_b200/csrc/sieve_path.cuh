@@ -56,6 +56,7 @@ constexpr int SV_THREADS = SV_THREADS_;
 constexpr int SV_CCAP = SV_CCAP_;                           // candidate blocks a pass aims at (its length is chosen accordingly)
 constexpr int SV_WQCAP = 160;                           // per-warp queue of blocks that passed the sieve: < 32 left over + <= 128 pushed
 constexpr int SV_PU = 4;                                // lists of one block resolved at a time (independent load chains)
+constexpr int SV_DYN_LEVELS = 2;                        // a dynamic pass rises from two lists to three and to four on its own
 constexpr int SV_SLOWCAP = 512;                         // blocks per pass that need the general resolution
 
 struct SieveShared {
@@ -82,7 +83,8 @@ struct SieveShared {
 	uint32_t promotedKey;
 	uint32_t bufCount, overflow, query, selPrefixLo, selK;
 	uint32_t nCand, nProbe, nSlow;
-	uint32_t dyn, nGe2, kWant, maxPos, switchGrp;       // dynamic pass (sieve_groups<2, true>): see there
+	uint32_t dyn, kWant, maxPos;                        // dynamic pass (sieve_groups<2, true>): see there
+	uint32_t nGe[SV_DYN_LEVELS], switchGrp[SV_DYN_LEVELS];      // candidates with >= 2 + i matches; from which group on 3 + i are needed
 	uint32_t tim[9];                                    // SV_TIMING: warp 0's cycles >> 6 in the sieve loads, the queue pushes, the resolve rounds, ...
 	uint32_t passG0, passG1, cRej, done;
 	uint32_t qlen, nGrams, cmin, cprom, nLists, sumMult;
@@ -101,13 +103,16 @@ __device__ __noinline__ void sieve_emit(SieveShared& sh, uint32_t term, uint32_t
 		if (key < tau) {
 			append_key(sh, key);
 			atomicAdd(&sh.geHist[c], 1u);
-			if (sh.dyn && atomicAdd(&sh.nGe2, 1u) + 1 == sh.kWant) {
-				// the k-th candidate with two or more matches of a dynamic pass: all k lie below the end of the furthest chunk
-				// any warp has started, so from there on a term needs three matches (chunks further down switch to c = 3)
-				const uint32_t x = *reinterpret_cast<volatile uint32_t*>(&sh.maxPos);
-				const unsigned long long xid = min(((unsigned long long)x * SIEVE_GROUP_BLOCKS) << sh.ix.sieveShift, 0xFFFFFFFFull);
-				atomicMin(&sh.tau, (((unsigned long long)sh.exactKey[2]) << 32) | xid);
-				*reinterpret_cast<volatile uint32_t*>(&sh.switchGrp) = x;
+			if (sh.dyn) {
+				// the k-th candidate with cc or more matches of a dynamic pass: all k lie below the end of the furthest chunk any
+				// warp has started, so from there on a term needs cc + 1 matches (chunks further down sieve for cc + 1 lists)
+				for (uint32_t cc = 2; cc <= min(c, 1u + SV_DYN_LEVELS); ++cc)
+					if (atomicAdd(&sh.nGe[cc - 2], 1u) + 1 == sh.kWant) {
+						const uint32_t x = *reinterpret_cast<volatile uint32_t*>(&sh.maxPos);
+						const unsigned long long xid = min(((unsigned long long)x * SIEVE_GROUP_BLOCKS) << sh.ix.sieveShift, 0xFFFFFFFFull);
+						atomicMin(&sh.tau, (((unsigned long long)sh.exactKey[cc]) << 32) | xid);
+						*reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[cc - 2]) = x;
+					}
 			}
 		}
 	} else {
@@ -386,7 +391,7 @@ __device__ __forceinline__ void sieve_step(const SieveShared& sh, const uint32_t
 }
 
 // DYN (CREQ == 2, the first phase of a query without threshold): the pass runs to the end of the id range and switches from
-// "two lists" to "three lists" on its own. Every warp publishes the end of the chunk it starts (maxPos); the candidate that
+// "two lists" to "three lists" (and, on indexes where even three-match terms are plentiful, on to "four") on its own. Every warp publishes the end of the chunk it starts (maxPos); the candidate that
 // brings the number of terms with two or more matches to k (sieve_emit) turns maxPos into the bound — k such terms lie below
 // it — and every chunk that starts at or behind it is sieved for three. One pass, and the two-list stretch is exactly as long
 // as the data needs (a planned pass is either too long: candidate blocks for nothing, or too short: another pass).
@@ -410,7 +415,8 @@ __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, co
 		if (DYN) {
 			if (lane == 0) atomicMax(&sh.maxPos, min(base + 64, g1));
 			__syncwarp();
-			if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp)) sieve_step<3, INL>(sh, nS, gA, gB, g1, m);
+			if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[1])) sieve_step<4, INL>(sh, nS, gA, gB, g1, m);
+			else if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[0])) sieve_step<3, INL>(sh, nS, gA, gB, g1, m);
 			else sieve_step<2, INL>(sh, nS, gA, gB, g1, m);
 		} else sieve_step<CREQ, INL>(sh, nS, gA, gB, g1, m);
 		uint32_t left = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]) + __popc(m[5]);
@@ -711,9 +717,12 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 						sh.dyn = dyn;
 						if (dyn) {
 							len = NG - gLo;
-							uint32_t ge2 = 0;
-							for (uint32_t c2 = 2; c2 <= nGrams; ++c2) ge2 += sh.geHist[c2];
-							sh.nGe2 = ge2; sh.kWant = k; sh.maxPos = gLo; sh.switchGrp = ge2 >= k ? gLo : 0xFFFFFFFFu;
+							sh.kWant = k; sh.maxPos = gLo;
+							for (uint32_t lv = 0; lv < (uint32_t)SV_DYN_LEVELS; ++lv) {
+								uint32_t ge = 0;
+								for (uint32_t c2 = 2 + lv; c2 <= nGrams; ++c2) ge += sh.geHist[c2];
+								sh.nGe[lv] = ge; sh.switchGrp[lv] = ge >= k ? gLo : 0xFFFFFFFFu;
+							}
 						}
 						sh.passG0 = gLo; sh.passG1 = min(NG, gLo + len);
 						sh.nCand = 0; sh.defCount = 0;
