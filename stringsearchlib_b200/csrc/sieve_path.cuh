@@ -56,7 +56,10 @@ constexpr int SV_THREADS = SV_THREADS_;
 constexpr int SV_CCAP = SV_CCAP_;                           // candidate blocks a pass aims at (its length is chosen accordingly)
 constexpr int SV_WQCAP = 160;                           // per-warp queue of blocks that passed the sieve: < 32 left over + <= 128 pushed
 constexpr int SV_PU = 4;                                // lists of one block resolved at a time (independent load chains)
-constexpr int SV_DYN_LEVELS = 2;                        // a dynamic pass rises from two lists to three and to four on its own
+#ifndef SV_DYN_LEVELS_
+#define SV_DYN_LEVELS_ 2
+#endif
+constexpr int SV_DYN_LEVELS = SV_DYN_LEVELS_;           // a dynamic pass rises from two lists to three, to four (and to five) on its own
 constexpr int SV_SLOWCAP = 512;                         // blocks per pass that need the general resolution
 
 struct SieveShared {
@@ -415,7 +418,8 @@ __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, co
 		if (DYN) {
 			if (lane == 0) atomicMax(&sh.maxPos, min(base + 64, g1));
 			__syncwarp();
-			if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[1])) sieve_step<4, INL>(sh, nS, gA, gB, g1, m);
+			if (SV_DYN_LEVELS >= 3 && base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[SV_DYN_LEVELS >= 3 ? 2 : 0])) sieve_step<5, INL>(sh, nS, gA, gB, g1, m);
+			else if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[1])) sieve_step<4, INL>(sh, nS, gA, gB, g1, m);
 			else if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[0])) sieve_step<3, INL>(sh, nS, gA, gB, g1, m);
 			else sieve_step<2, INL>(sh, nS, gA, gB, g1, m);
 		} else sieve_step<CREQ, INL>(sh, nS, gA, gB, g1, m);
