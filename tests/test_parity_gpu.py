@@ -149,6 +149,26 @@ def test_c1_ascii_rowsize1(ssb, oracle_built, n, nq, th, limit):
         assert st["nFast"] == 8 and st["nDense"] == 0
 
 
+def test_sieve_16_byte_layout_without_threshold(ssb, oracle_built, monkeypatch):
+    """indexes of more than 32M terms have only the 16-byte sieve groups (index.h): their path through k_sieve_search at threshold 0
+    (dynamic pass, postings read for every candidate block) is forced here on a small index with SSB_SIEVE_INLINE=0."""
+    from stringsearchlib_b200 import synth
+    monkeypatch.setenv("SSB_SIEVE_INLINE", "0")
+    keys = synth.ascii_keys(200000)
+    S = oracle_built.SpecIndex(keys, 1)
+    with ssb.Index(keys, 1) as ix:
+        _, o = check_tables(ix, S)
+        q = synth.queries_from(keys, 256)
+        check_search(ix, S, q, 0.0, 100, o)
+        check_search(ix, S, q, 0.0, 10, o)
+        check_search(ix, S, q, 0.3, 500, o)
+    monkeypatch.delenv("SSB_SIEVE_INLINE")
+    with ssb.Index(keys, 1) as ix:                      # and the default (both layouts) on the same inputs
+        _, o = check_tables(ix, S)
+        check_search(ix, S, q, 0.0, 10, o)
+        check_search(ix, S, q, 0.3, 500, o)
+
+
 def test_c2_rowsize2_weights(ssb, oracle_built):
     """C2 shape (scaled): rows (key, description), per-word weights, threshold 0.3 and 0."""
     from stringsearchlib_b200 import synth
