@@ -5,23 +5,27 @@
 // query are first looked at through their block bitmaps (sieve.cu): one bit per block of 2^shift consecutive term ids. With
 // tau the running k-th best (or the threshold, hpp:313-316) a term needs c = cRej + 1 matches to matter, and it can only
 // have them inside a block in which at least c of the K bitmaps have their bit set. Per pass over a range of bitmap words:
-//   SIEVE    every thread streams two 32-block words of each list (one coalesced 8-byte load per list, all K in flight)
-//            through the bit-sliced threshold counter  ge[c] |= ge[c-1] & x  (c LOP3 per word and list): ge[c-1] = blocks
-//            hit by >= c lists. The numbers of the blocks that pass are queued (one warp scan + one shared atomic per warp).
-//   RESOLVE  one thread per queued block: which lists hit it (their words are still in L1/L2), then for up to four lists at a
-//            time the rank of the block inside its 256-block group (popcount of the lower bits of the group's 8 words) + the
-//            group's directory entry = position of the block's first posting, which is read from the bit-exact CSR postings
-//            (a second posting of the same list in the block, rare, follows it). The terms found are counted in registers —
-//            the reference's match count, with multiplicities — filtered by the integer bound derived from tau and handed to
-//            the same emit / deferred-evaluation code as k_fast_search.
+//   SIEVE    every lane streams two 96-block groups of each list (one coalesced 16-byte load per group: first posting + block
+//            bits) through the bit-sliced threshold counter  ge[c] |= ge[c-1] & x  (c LOP3 per word and list): ge[c-1] = blocks
+//            hit by >= c lists. The numbers of the blocks that pass are queued (one warp scan per step, a queue per warp).
+//   RESOLVE  one thread per queued block, a warp of blocks at a time: which lists hit it (their words are still in L1/L2), then
+//            for up to four lists the block's rank among the occupied blocks of its group (popcount of the lower bits).
+//            INL (32-byte groups, index.h): the rank selects the group's slot = the offset of the list's posting inside the
+//            block, so block number + offset is the term id and no posting is read. !INL (16-byte groups): group's first
+//            posting + rank = position of the block's first posting in the bit-exact CSR postings, three of which are read.
+//            The terms found are counted in registers — the reference's match count, with multiplicities — filtered by the
+//            integer bound derived from tau and handed to the same emit / deferred-evaluation code as k_fast_search. Blocks
+//            in which a list has several postings, or that more than four lists hit, go to the general resolution
+//            (resolve_slow), which walks the postings.
 // Passes run in ascending term-id order; tau moves from class to class through bounds that cost nothing (k candidates with
 // >= c matches are known, all below the end of the pass), so that c rises and the sieve gets sparser as the query proceeds.
 // On identity indexes without threshold the terms with ONE match are left for last: the first phase looks for terms with
 // two or more matches only (no seeding pass over every posting of the smallest ids), and only if fewer than k exist does a
 // second phase fill the list with the smallest single-match ids.
-// Bytes read per query: K bitmaps (~ the bytes of the K lists at the chosen block size) + ~100 B per (block, list) resolved,
-// against 4 bytes + ~150 instructions per posting for the merge. Exactness does not depend on the bitmaps being selective:
-// a block that passes is resolved from the postings themselves.
+// Bytes read per query: K bitmaps (16 or 32 bytes per 96 blocks: 1.3x / 2.5x the bytes of the K lists at the chosen block size;
+// + one 32-byte sector per (block, list) resolved when !INL), against 4 bytes + ~150 instructions per posting for the merge.
+// Exactness does not depend on the bitmaps being selective: a block that passes is resolved from the postings themselves or
+// from slots that restate them exactly (sieve.cu), and a disagreement between bits and postings hands the query over.
 // Queries the kernel does not take (a list without bitmap, more than 16 lists, the edit-distance path) or cannot finish
 // (candidate buffer too small for one 64-block step, more than 8 distinct terms of interest in one block) are handed to
 // k_fast_search through handList.
