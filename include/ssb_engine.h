@@ -17,7 +17,8 @@ uint64_t ssb_kernel_launches(void);
 /* binds the engine to a CUDA device (default: current device). Call once per process, before any index. */
 int ssb_set_device(int device);
 /* which kernel answers the queries of the batched fast path: 1 = k_sieve_search for every query it can take (block bitmaps
- * over the posting lists; reads only the postings of blocks that can still matter), the rest k_fast_search; 0 = k_fast_search
+ * over the posting lists; resolves only the blocks that can still matter, from posting offsets stored next to the
+ * bits or from the postings themselves), the rest k_fast_search; 0 = k_fast_search
  * alone (register K-way merge of the posting lists); -1 = the default: per query, k_sieve_search from 20 000 postings up
  * (environment: SSB_SIEVE_MIN_POSTINGS) and k_fast_search below — the sieve pays a fixed price per query and then grows
  * slowly with the lists, the merge grows with every posting (0 when the environment variable SSB_MERGE is set). Results are
