@@ -60,6 +60,12 @@ constexpr int SV_THREADS = SV_THREADS_;
 constexpr int SV_CCAP = SV_CCAP_;                           // candidate blocks a pass aims at (its length is chosen accordingly)
 constexpr int SV_WQCAP = 160;                           // per-warp queue of blocks that passed the sieve: < 32 left over + <= 128 pushed
 constexpr int SV_PU = 4;                                // lists of one block resolved at a time (independent load chains)
+// -DSV_DYN16=1: a dynamic pass over the 32-byte layout streams the 16-byte one behind its first rise (half the bytes, but the
+// blocks that pass read their postings again). Measured slower: 0.71 vs 0.60 ms per batch at 10M keys — the scattered reads cost
+// more than the stream saves even at three lists.
+#ifndef SV_DYN16
+#define SV_DYN16 0
+#endif
 #ifndef SV_DYN_LEVELS_
 #define SV_DYN_LEVELS_ 2
 #endif
@@ -69,6 +75,7 @@ constexpr int SV_SLOWCAP = 512;                         // blocks per pass that 
 struct SieveShared {
 	const uint4* sievePtr[SV_MAXL];                     // group arrays as the sieve counts them: list j repeated mult[j] times
 	const uint4* grpPtr[SV_MAXL];                       // group array of list j: { first posting, 3 x 32 block bits } per 96 blocks
+	const uint4* sievePtr16[SV_MAXL], *grpPtr16[SV_MAXL];      // the same in the 16-byte layout (k_sieve_search<U, false>: equal to the two above)
 	uint32_t listEnd[SV_MAXL], mult[SV_MAXL];
 	uint32_t wq[SV_THREADS / 32][SV_WQCAP];             // numbers of the blocks that passed the sieve, per warp
 	uint32_t slowQ[SV_SLOWCAP];                         // of those, the ones left to resolve_slow
@@ -144,6 +151,7 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 {
 	constexpr int CAP = 48;
 	constexpr uint32_t GU = INL ? 2 : 1;                     // 16-byte units per group
+	const uint4* const* const gp = INL ? sh.grpPtr : sh.grpPtr16;
 	const int shift = sh.ix.sieveShift;
 	const uint32_t* __restrict__ postings = sh.ix.postings;
 	const uint32_t v = blk >> 5, g = v / 3u, k = v - 3u * g, bit = blk & 31u;
@@ -163,7 +171,7 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 #define SV_TICKS(slot) do { } while (0)
 #endif
 #pragma unroll 4
-	for (uint32_t j = 0; j < nL; ++j) lm |= ((__ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + GU * g) + 1 + k) >> bit) & 1u) << j;
+	for (uint32_t j = 0; j < nL; ++j) lm |= ((__ldg(reinterpret_cast<const uint32_t*>(gp[j] + GU * g) + 1 + k) >> bit) & 1u) << j;
 	unsigned long long ent[CAP];                             // (multiplicity, term id) of every posting inside the block
 	uint32_t m = 0;
 	SV_TICKS(5);
@@ -174,12 +182,12 @@ __device__ __noinline__ void resolve_slow(SieveShared& sh, uint32_t blk, uint32_
 	while (lm) {
 		const uint32_t j = (uint32_t)__ffs(lm) - 1u;
 		lm &= lm - 1;
-		const uint4 x = __ldg(sh.grpPtr[j] + GU * g);
+		const uint4 x = __ldg(gp[j] + GU * g);
 		const uint32_t end = sh.listEnd[j], mu = sh.mult[j];
 		// a list with one posting in the block: its slot of the same sector says which term (no posting read)
 		const uint32_t r = __popc(x.y & my) + __popc(x.z & mz) + __popc(x.w & mw);
 		if (INL && r < nSlot) {
-			const uint32_t* sp = reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + GU * g + 1);
+			const uint32_t* sp = reinterpret_cast<const uint32_t*>(gp[j] + GU * g + 1);
 			const uint32_t wd = (r * bps) >> 5;
 			const uint32_t s0 = __ldg(sp + wd), s1 = wd < 3 ? __ldg(sp + wd + 1) : 0u;
 			const uint32_t v = __funnelshift_r(s0, s1, (r * bps) & 31u) & ((1u << bps) - 1u);
@@ -245,6 +253,7 @@ template <bool INL>
 __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t blk, const uint32_t onlyCount, const unsigned long long tau)
 {
 	constexpr uint32_t GU = INL ? 2 : 1;
+	const uint4* const* const gp = INL ? sh.grpPtr : sh.grpPtr16;
 	const int shift = sh.ix.sieveShift;
 	const uint32_t* __restrict__ postings = sh.ix.postings;
 	const uint32_t nL = sh.nLists;
@@ -257,7 +266,7 @@ __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t b
 		uint32_t wv[SV_MAXL];
 #pragma unroll
 		for (int j = 0; j < SV_MAXL; ++j)
-			wv[j] = (uint32_t)j < nL ? __ldg(reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + GU * g) + 1 + k) : 0u;
+			wv[j] = (uint32_t)j < nL ? __ldg(reinterpret_cast<const uint32_t*>(gp[j] + GU * g) + 1 + k) : 0u;
 #pragma unroll
 		for (int j = 0; j < SV_MAXL; ++j) lm |= ((wv[j] >> bit) & 1u) << j;
 	}
@@ -279,7 +288,7 @@ __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t b
 	#pragma unroll
 			for (int u = 0; u < SV_PU; ++u) {
 				const uint32_t j = rest ? (uint32_t)__ffs(rest) - 1u : 0u;
-				x[u] = rest ? __ldg(sh.grpPtr[j] + GU * g) : make_uint4(0, 0, 0, 0);
+				x[u] = rest ? __ldg(gp[j] + GU * g) : make_uint4(0, 0, 0, 0);
 				jp |= j << (4 * u);
 				rest &= rest - 1;
 			}
@@ -293,7 +302,7 @@ __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t b
 				const uint32_t j = (jp >> (4 * u)) & 15u;
 				const bool on = (uint32_t)u < ns && rk[u] < nSlot;
 				const uint32_t wd = (rk[u] * bps) >> 5;
-				const uint32_t* sp = reinterpret_cast<const uint32_t*>(sh.grpPtr[j] + GU * g + 1);
+				const uint32_t* sp = reinterpret_cast<const uint32_t*>(gp[j] + GU * g + 1);
 				s0[u] = on ? __ldg(sp + wd) : 0u;
 				s1[u] = on && wd < 3 ? __ldg(sp + wd + 1) : 0u;
 				mu[u] = sh.mult[j];
@@ -316,7 +325,7 @@ __device__ __noinline__ uint32_t resolve_block(SieveShared& sh, const uint32_t b
 	#pragma unroll
 			for (int u = 0; u < SV_PU; ++u) {
 				const uint32_t j = rest ? (uint32_t)__ffs(rest) - 1u : 0u;
-				x[u] = rest ? __ldg(sh.grpPtr[j] + GU * g) : make_uint4(0, 0, 0, 0);
+				x[u] = rest ? __ldg(gp[j] + GU * g) : make_uint4(0, 0, 0, 0);
 				jp |= j << (4 * u);
 				rest &= rest - 1;
 			}
@@ -384,7 +393,7 @@ __device__ __forceinline__ void sieve_step(const SieveShared& sh, const uint32_t
 	const bool onA = gA < g1, onB = gB < g1;
 #pragma unroll 4
 	for (uint32_t j = 0; j < nS; ++j) {
-		const uint4* ptr = sh.sievePtr[j];
+		const uint4* ptr = (INL ? sh.sievePtr : sh.sievePtr16)[j];
 		const uint4 x = onA ? __ldg(ptr + GU * gA) : make_uint4(0, 0, 0, 0);      // { first posting, 3 x 32 block bits }
 		const uint4 y = onB ? __ldg(ptr + GU * gB) : make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -422,9 +431,10 @@ __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, co
 		if (DYN) {
 			if (lane == 0) atomicMax(&sh.maxPos, min(base + 64, g1));
 			__syncwarp();
-			if (SV_DYN_LEVELS >= 3 && base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[SV_DYN_LEVELS >= 3 ? 2 : 0])) sieve_step<5, INL>(sh, nS, gA, gB, g1, m);
-			else if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[1])) sieve_step<4, INL>(sh, nS, gA, gB, g1, m);
-			else if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[0])) sieve_step<3, INL>(sh, nS, gA, gB, g1, m);
+			// (SV_DYN16: the 16-byte layout behind the first rise; default: the kernel's own layout throughout)
+			if (SV_DYN_LEVELS >= 3 && base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[SV_DYN_LEVELS >= 3 ? 2 : 0])) sieve_step<5, INL && !SV_DYN16>(sh, nS, gA, gB, g1, m);
+			else if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[1])) sieve_step<4, INL && !SV_DYN16>(sh, nS, gA, gB, g1, m);
+			else if (base >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[0])) sieve_step<3, INL && !SV_DYN16>(sh, nS, gA, gB, g1, m);
 			else sieve_step<2, INL>(sh, nS, gA, gB, g1, m);
 		} else sieve_step<CREQ, INL>(sh, nS, gA, gB, g1, m);
 		uint32_t left = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]) + __popc(m[5]);
@@ -463,7 +473,10 @@ __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, co
 				const uint32_t blk = wq[qn + lane];
 				__syncwarp();
 				if (DYN) tau = *reinterpret_cast<volatile unsigned long long*>(&sh.tau);      // (it tightens while the pass runs)
-				np += resolve_block<INL>(sh, blk, onlyCount, tau);
+				// (either layout resolves a block exactly; the one whose sectors the warp has just streamed is the cheap one)
+				if (DYN && INL && SV_DYN16 && blk / SIEVE_GROUP_BLOCKS >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[0]))
+					np += resolve_block<false>(sh, blk, onlyCount, tau);
+				else np += resolve_block<INL>(sh, blk, onlyCount, tau);
 			}
 			SV_TICKW(2);
 		}
@@ -471,7 +484,11 @@ __device__ __noinline__ void sieve_groups(SieveShared& sh, const uint32_t g0, co
 	if (qn) {
 		const uint32_t blk = (uint32_t)lane < qn ? wq[lane] : INF;
 		if (DYN) tau = *reinterpret_cast<volatile unsigned long long*>(&sh.tau);
-		if (blk != INF) np += resolve_block<INL>(sh, blk, onlyCount, tau);
+		if (blk != INF) {
+			if (DYN && INL && SV_DYN16 && blk / SIEVE_GROUP_BLOCKS >= *reinterpret_cast<volatile uint32_t*>(&sh.switchGrp[0]))
+				np += resolve_block<false>(sh, blk, onlyCount, tau);
+			else np += resolve_block<INL>(sh, blk, onlyCount, tau);
+		}
 	}
 #pragma unroll
 	for (int o = 16; o; o >>= 1) { nc += __shfl_xor_sync(0xffffffffu, nc, o); np += __shfl_xor_sync(0xffffffffu, np, o); }
@@ -573,9 +590,10 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 		if (tid < SV_MAXL) {
 			if ((uint32_t)tid < nLists) {
 				sh.grpPtr[tid] = sieveBase + (size_t)d.listSlot[tid] * NG * GU;
+				sh.grpPtr16[tid] = ix.sieveGroups + (size_t)d.listSlot[tid] * NG;
 				sh.listEnd[tid] = d.listOff[tid] + d.listLen[tid];
 				sh.mult[tid] = d.listMult[tid];
-			} else { sh.grpPtr[tid] = sieveBase; sh.listEnd[tid] = 0; sh.mult[tid] = 0; }
+			} else { sh.grpPtr[tid] = sieveBase; sh.grpPtr16[tid] = ix.sieveGroups; sh.listEnd[tid] = 0; sh.mult[tid] = 0; }
 		} else if (tid >= 32 && tid < 32 + 9) {
 			const uint32_t c = tid - 32;
 			sh.rateTab[c] = fmaxf(3.0f * sieve_rate(nLists, max(c, 1u), dens), 1e-4f);      // per 96-block group
@@ -610,7 +628,10 @@ __global__ void __launch_bounds__(SV_THREADS, SV_MIN_CTAS) k_sieve_search(IndexV
 			uint32_t sum = 0;
 			for (uint32_t i = 0; i < nLists; ++i)
 				for (uint32_t r = 0; r < d.listMult[i]; ++r) {
-					if (sum < SV_MAXL) sh.sievePtr[sum] = sieveBase + (size_t)d.listSlot[i] * NG * GU;
+					if (sum < SV_MAXL) {
+						sh.sievePtr[sum] = sieveBase + (size_t)d.listSlot[i] * NG * GU;
+						sh.sievePtr16[sum] = ix.sieveGroups + (size_t)d.listSlot[i] * NG;
+					}
 					++sum;
 				}
 			sh.sumMult = sum;
